@@ -1,0 +1,231 @@
+"""HVNet / HPNet / HTNet on the B200-native hot path.
+
+Drop-in for ``/root/reference/HermNet/hermnet.py``: same class names, constructor arguments, ``forward(data)``
+signature (-> energy per graph, attached to autograd so that ``torch.autograd.grad(E.sum(), data.pos)`` gives
+forces) and ``state_dict`` layout (``embed``, ``radial_basis``, ``hermconvs.{l}.mods.{name}``, ``out_energy``).
+HPNet and HTNet do not exist in the reference (``HTNet.__init__`` raises, hermnet.py:155-157); they follow the
+builder-owned specification of SURVEY.md A.3.
+
+What changed underneath (hermnet.py:37-65,118-152 + utils.py:11-24 + rmnet.py:51-73):
+  * the per-element Python loop with ``in_subgraph`` is replaced by ONE row-CSR graph (``graph.RowGraph``);
+  * edge geometry, RBF x envelope, filter projection, gathers, messages and the scatter-add are one fused CUDA
+    kernel per layer (``functional.painn_edge``) with hand-written backward kernels;
+  * node-side MLPs run on the element-type slices that survive ``vrsts[nid] += vrst[nid]`` (hermnet.py:60-61)
+    instead of on all N nodes per element -- value-identical, T-fold less work.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Union
+
+import torch
+from torch import nn
+
+from . import functional as Fn
+from . import ops
+from .graph import GraphBuilder, RowGraph, pair_list
+from .rmnet import PaiNNModule, RadialBasis, ScaledSiLU
+from .symbols import atomic_numbers
+
+__all__ = ["HVNet", "HPNet", "HTNet", "HeteroVertexConv", "HeteroPairConv", "HeteroTriadConv"]
+
+
+class HeteroVertexConv(nn.Module):
+    """Container of the per-element sub-networks of one layer (hermnet.py:11-35): ``mods[element]``."""
+
+    def __init__(self, mods: Dict[str, nn.Module]):
+        super().__init__()
+        self.mods = nn.ModuleDict(mods)
+
+
+class HeteroPairConv(HeteroVertexConv):
+    """Per ordered element pair ``"src-dst"`` (figs/arch.svg (c))."""
+
+
+class HeteroTriadConv(HeteroVertexConv):
+    """Per triad ``"A-centre-C"``, A <= C in constructor order (figs/arch.svg (d))."""
+
+
+class _HermNet(nn.Module):
+    KIND = "HVNet"
+    CONV = HeteroVertexConv
+
+    def __init__(self, elems: Union[str, List[str]], rc: float = 5., intensive: bool = False, num_layers: int = 5,
+                 hidden_channels: int = 512, num_rbf: int = 128, rbf={"name": "gaussian"},
+                 envelope={"name": "polynomial", "exponent": 5}, pbc_shift: str = "reference"):
+        super().__init__()
+        self.elems = [elems] if isinstance(elems, str) and elems in atomic_numbers else list(elems)
+        self.rc = float(rc)           # superset of the reference: the plugins read ``model.rc`` (calculator.py:49)
+        self.num_layers = num_layers
+        self.hidden_channels = hidden_channels
+        self.num_rbf = num_rbf
+        self.intensive = intensive
+        self.pbc_shift = pbc_shift
+        self.edge_path = "auto"       # 'auto' | 'fused' | 'composite'
+        self.store_features = False   # write data.x / data.vec back like the reference does (hermnet.py:63-64)
+
+        self.embed = nn.Embedding(len(atomic_numbers), hidden_channels)
+        self.radial_basis = RadialBasis(num_radial=num_rbf, cutoff=rc, rbf=rbf, envelope=envelope)
+        self.hermconvs = nn.ModuleList()
+        for _ in range(num_layers):
+            self.hermconvs.append(self.CONV(mods={name: PaiNNModule(hidden_channels=hidden_channels, num_rbf=num_rbf)
+                                                  for name in self.module_names()}))
+        self.out_energy = nn.Sequential(nn.Linear(hidden_channels, hidden_channels // 2), ScaledSiLU(),
+                                        nn.Linear(hidden_channels // 2, 1))
+        self.builder = GraphBuilder(self.KIND, self.elems, self.rc, pbc_shift)
+
+    # ------------------------------------------------------------------------------------------------
+    def module_names(self) -> List[str]:
+        e = self.elems
+        if self.KIND == "HVNet":
+            return list(e)
+        if self.KIND == "HPNet":
+            return [f"{s}-{d}" for d in e for s in e]
+        pairs = pair_list(len(e))
+        return [f"{e[a]}-{t}-{e[c]}" for t in e for (a, c) in pairs]
+
+    def build_graph(self, pos, atomic_number, cell=None, batch=None) -> RowGraph:
+        """Device neighbour search + row CSR for this model (replaces data.py:14-24 and utils.py:11-24)."""
+        return self.builder.from_positions(pos, atomic_number, cell, batch)
+
+    def _graph_of(self, data) -> RowGraph:
+        g = data.get("graph") if hasattr(data, "get") else getattr(data, "graph", None)
+        n = data.pos.size(0)
+        if isinstance(g, RowGraph) and g.kind == self.KIND and g.n_atoms == n and g.sign == self.builder.sign:
+            return g
+        batch = data.get("batch")
+        ei = data.get("edge_index")
+        if ei is not None:
+            g = self.builder.from_edge_index(data.atomic_number, ei, data.get("edge_shift"), batch)
+        else:
+            g = self.builder.from_positions(data.pos, data.atomic_number, data.get("cell"), batch)
+        data.graph = g
+        return g
+
+    def _use_fused(self, pos) -> bool:
+        if self.edge_path == "fused":
+            return True
+        if self.edge_path == "composite":
+            return False
+        return (not self.training) and self.radial_basis.fusable() and self.hidden_channels % 32 == 0 \
+            and pos.dtype == torch.float32
+
+    # ------------------------------------------------------------------------------------------------
+    def forward(self, data):
+        pos = data.pos
+        ops.require_cuda(pos, f"{self.KIND}.forward")
+        g = self._graph_of(data)
+        cell = data.get("cell")
+        if cell is not None and data.get("edge_shift") is None and data.get("edge_index") is not None:
+            cell = None               # hermnet.py:138: the shift term needs both cell and edge_shift
+        if cell is not None:
+            cell = cell.reshape(-1, 3, 3)
+        energy, x, vec = self.forward_graph(pos, data.atomic_number, cell, g)
+        if self.store_features:
+            data.x, data.vec = x[g.inv_perm], vec[g.inv_perm]
+        return energy
+
+    def forward_graph(self, pos, atomic_number, cell, g: RowGraph):
+        """Hot path on a prebuilt ``RowGraph``: energies ``[num_graphs]`` plus final features (internal order)."""
+        F = self.hidden_channels
+        fused = self._use_fused(pos)
+        pos_i = pos[g.perm]
+        z_i = atomic_number[g.perm].long()
+        if fused:
+            geom = Fn.edge_geometry(pos_i, cell, g)
+            gs = self.radial_basis.rbf
+            p = ops.edge_params(g, g.n_modules, F, self.num_rbf, int(self.radial_basis.envelope.p), self.rc, gs.coeff)
+        else:
+            geom = Fn.edge_geometry_composite(pos_i, cell, g)
+            p = None
+        x = self.embed(z_i)
+        vec = torch.zeros((x.size(0), 3, F), dtype=x.dtype, device=x.device)
+        for conv in self.hermconvs:
+            x, vec = self._layer(conv, x, vec, geom, g, p)
+        e_atom = self.out_energy(x)                                      # [N,1]   hermnet.py:129
+        energy = Fn.segment_sum(e_atom, g.seg_batch).squeeze(1)          # hermnet.py:130
+        if self.intensive:
+            sb = g.seg_batch
+            energy = energy / (sb.rowptr[1:] - sb.rowptr[:-1]).clamp(min=1).to(energy.dtype)
+        return energy, x, vec
+
+    # ------------------------------------------------------------------------------------------------
+    def _layer(self, conv, x, vec, geom, g: RowGraph, p):
+        F = self.hidden_channels
+        mods = list(conv.mods.values())
+        # node side, part 1: projected source features of every sub-network, compact (graph.xh_sources)
+        blocks = []
+        for mod, srcs in zip(mods, g.xh_sources):
+            rows = x[srcs[0][0]:srcs[0][1]] if len(srcs) == 1 else torch.cat([x[lo:hi] for lo, hi in srcs], 0)
+            blocks.append(mod.message_layer.node_features(rows))
+        xh = torch.cat(blocks, 0)                                        # [rows, 3F]
+        Wt = torch.stack([m.message_layer.rbf_proj.weight.t() for m in mods])   # [M,K,3F]
+        bias = torch.stack([m.message_layer.rbf_proj.bias for m in mods])       # [M,3F]
+        # edge side
+        if p is not None:
+            dx, dvec = Fn.painn_edge(xh, vec, geom, Wt, bias, self.radial_basis.rbf.offset, g, p)
+        else:
+            dx, dvec = Fn.painn_edge_composite_flat(xh, vec, geom, Wt, bias, self.radial_basis, g)
+        # node side, part 2: residual + update on the destination-element slices
+        R = g.rows_per_atom
+        dx = dx.view(-1, R, F)
+        dvec = dvec.view(-1, R, 3, F)
+        T = len(self.elems)
+        xs, vs = [], []
+        for t in range(T):
+            sl = g.type_slice(t)
+            if sl.stop == sl.start:
+                continue
+            xt, vt = x[sl], vec[sl]
+            x_acc = v_acc = None
+            for m, slots in self._dst_modules(t):
+                mod = mods[m]
+                if self.KIND == "HTNet":
+                    pa = dvec[sl, slots[0]]
+                    pc = dvec[sl, slots[1]] if slots[1] != slots[0] else pa
+                    dxm = dx[sl, slots[0]] + (dx[sl, slots[1]] if slots[1] != slots[0] else 0)
+                    dvm = pa + pc if slots[1] != slots[0] else pa
+                    na = torch.sqrt((pa ** 2).sum(dim=1) + 1e-8)
+                    nc = torch.sqrt((pc ** 2).sum(dim=1) + 1e-8)
+                    vdot = (pa * pc).sum(dim=1) / (na * nc)
+                else:
+                    dxm, dvm, vdot = dx[sl, slots[0]], dvec[sl, slots[0]], None
+                v_new, x_new = mod.node_update(xt, vt, dxm, dvm, vdot)
+                act = g.mod_active[m]                                    # hermnet.py:56-57: no edges -> rows stay 0
+                x_acc = x_new * act if x_acc is None else x_acc + x_new * act
+                v_acc = v_new * act if v_acc is None else v_acc + v_new * act
+            xs.append(x_acc)
+            vs.append(v_acc)
+        n_unknown = g.type_ptr[T + 1] - g.type_ptr[T]
+        if n_unknown:
+            xs.append(torch.zeros((n_unknown, F), dtype=x.dtype, device=x.device))
+            vs.append(torch.zeros((n_unknown, 3, F), dtype=x.dtype, device=x.device))
+        return torch.cat(xs, 0), torch.cat(vs, 0)
+
+    def _dst_modules(self, t: int):
+        """(module id, row slots) of the sub-networks whose destination element is ``t``."""
+        T = len(self.elems)
+        if self.KIND == "HVNet":
+            return [(t, (0, 0))]
+        if self.KIND == "HPNet":
+            return [(t * T + s, (s, s)) for s in range(T)]
+        pairs = pair_list(T)
+        return [(t * len(pairs) + i, (2 * i, 2 * i if a == c else 2 * i + 1)) for i, (a, c) in enumerate(pairs)]
+
+
+class HVNet(_HermNet):
+    """Heterogeneous Vertex Network (hermnet.py:68-131): one sub-network per destination element."""
+    KIND = "HVNet"
+    CONV = HeteroVertexConv
+
+
+class HPNet(_HermNet):
+    """Heterogeneous Pair Network: one sub-network per ordered element pair, summed into the destination."""
+    KIND = "HPNet"
+    CONV = HeteroPairConv
+
+
+class HTNet(_HermNet):
+    """Heterogeneous Triadic Network: one sub-network per (centre, {A, C}) with the angular inner product
+    <sum_{j in A} m_ij / |.|, sum_{k in C} m_ik / |.|> -- the factorised sum over triplets (j, i, k)."""
+    KIND = "HTNet"
+    CONV = HeteroTriadConv

@@ -1,0 +1,298 @@
+"""Tensor-level wrappers over the C ABI (``include/hermnet_b200.h``).
+
+Each function takes CUDA torch tensors (torch is only the owner of device memory and of the stream),
+passes raw pointers + the current stream through ctypes and returns freshly allocated outputs.  There is
+no CPU implementation: a non-CUDA tensor raises.  The autograd layer (``functional.py``) and the graph
+builder (``graph.py``) call these through the module namespace (``ops.<name>``).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import EdgeParams
+
+Tensor = torch.Tensor
+
+
+def _ptr(t: Optional[Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(dev) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _chk(name: str, *tensors, dtype=None):
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError(f"hermnet_b200.{name}: expected a CUDA tensor, got device={t.device}; "
+                               "the hot path has no CPU fallback")
+        if not t.is_contiguous():
+            raise RuntimeError(f"hermnet_b200.{name}: tensors must be contiguous")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"hermnet_b200.{name}: tensors on different devices")
+    return dev
+
+
+def _f32(name, *ts):
+    for t in ts:
+        if t is not None and t.dtype != torch.float32:
+            raise RuntimeError(f"hermnet_b200.{name}: float tensors must be float32 (got {t.dtype})")
+
+
+def _i32(name, *ts):
+    for t in ts:
+        if t is not None and t.dtype != torch.int32:
+            raise RuntimeError(f"hermnet_b200.{name}: index tensors must be int32 (got {t.dtype})")
+
+
+def require_cuda(t: Tensor, what: str) -> None:
+    """Loud failure for CPU inputs: the product has no CPU path (tests swap this module's functions for an
+    emulator that lives under tests/, never the other way round)."""
+    if not t.is_cuda:
+        raise RuntimeError(f"{what}: data is on {t.device}; the hermnet_b200 hot path runs on CUDA only "
+                           "(there is no CPU fallback) -- move the inputs to a CUDA device")
+
+
+def compute_device(t: Tensor) -> torch.device:
+    """Device the kernels will run on for an input living on ``t.device`` (CPU inputs are staged to the GPU)."""
+    if t.is_cuda:
+        return t.device
+    if not torch.cuda.is_available():
+        raise RuntimeError("hermnet_b200 needs a CUDA device (there is no CPU fallback)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def sm_count() -> int:
+    return int(_lib.load().hn_device_sm_count())
+
+
+# ----------------------------------------------------------------------------------------------------
+# graph construction
+# ----------------------------------------------------------------------------------------------------
+def radius_graph(pos: Tensor, cell: Optional[Tensor], graph_ptr: Tensor, rc: float, group: Optional[Tensor] = None,
+                 n_groups: int = 1, max_neighbors: int = 0) -> Tuple[Tensor, Tensor, Tensor]:
+    """Row CSR of the neighbour list: row ``c*n_groups+g`` = neighbours ``(j, S)`` of centre ``c`` in group ``g``.
+    Returns ``rowptr int32 [N*n_groups+1]``, ``col int32 [E]``, ``shift int8 [E,4]``.  One host sync (E)."""
+    lib = _lib.load()
+    dev = _chk("radius_graph", pos, cell, graph_ptr, group)
+    _f32("radius_graph", pos, cell)
+    _i32("radius_graph", graph_ptr, group)
+    n = pos.size(0)
+    n_graphs = graph_ptr.numel() - 1
+    with torch.cuda.device(dev):
+        ws_bytes = int(lib.hn_radius_graph_workspace_bytes(n, n_graphs))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        counts = torch.empty(n * n_groups, dtype=torch.int32, device=dev)
+        st = _stream(dev)
+        _lib.check(lib.hn_radius_graph_count(_ptr(pos), n, _ptr(cell), _ptr(graph_ptr), n_graphs, float(rc), _ptr(group),
+                                             n_groups, max_neighbors, _ptr(counts), _ptr(ws), ws_bytes, st),
+                   "hn_radius_graph_count")
+        rowptr = torch.zeros(n * n_groups + 1, dtype=torch.int32, device=dev)
+        torch.cumsum(counts, 0, dtype=torch.int32, out=rowptr[1:])
+        n_edges = int(rowptr[-1].item())
+        col = torch.empty(n_edges, dtype=torch.int32, device=dev)
+        shift = torch.empty((n_edges, 4), dtype=torch.int8, device=dev)
+        if n_edges > 0:
+            _lib.check(lib.hn_radius_graph_fill(_ptr(pos), n, _ptr(cell), _ptr(graph_ptr), n_graphs, float(rc), _ptr(group),
+                                                n_groups, max_neighbors, _ptr(rowptr), _ptr(col), _ptr(shift), _ptr(ws),
+                                                ws_bytes, st), "hn_radius_graph_fill")
+    return rowptr, col, shift
+
+
+def sort_by_key(keys: Tensor, n_keys: int) -> Tuple[Tensor, Tensor]:
+    """Stable grouping of ``arange(len(keys))`` by key: ``rowptr int32 [n_keys+1]``, ``order int32 [n]``."""
+    lib = _lib.load()
+    dev = _chk("sort_by_key", keys)
+    _i32("sort_by_key", keys)
+    n = keys.numel()
+    with torch.cuda.device(dev):
+        ws_bytes = int(lib.hn_sort_by_key_workspace_bytes(n, n_keys))
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        rowptr = torch.empty(n_keys + 1, dtype=torch.int32, device=dev)
+        order = torch.empty(n, dtype=torch.int32, device=dev)
+        _lib.check(lib.hn_sort_by_key(_ptr(keys), n, n_keys, _ptr(rowptr), _ptr(order), _ptr(ws), ws_bytes, _stream(dev)),
+                   "hn_sort_by_key")
+    return rowptr, order
+
+
+def expand_rowptr(rowptr: Tensor, n_edges: int) -> Tensor:
+    lib = _lib.load()
+    dev = _chk("expand_rowptr", rowptr)
+    _i32("expand_rowptr", rowptr)
+    out = torch.empty(n_edges, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.hn_expand_rowptr(_ptr(rowptr), rowptr.numel() - 1, _ptr(out), _stream(dev)), "hn_expand_rowptr")
+    return out
+
+
+def triplets(rowptr: Tensor, col: Tensor, src_type: Optional[Tensor] = None, type_a: int = -1, type_c: int = -1):
+    """Canonical ordered triplets over row-edge ids: ``trip_ptr int64 [R+1]``, ``e1``, ``e2`` int32 [T]."""
+    lib = _lib.load()
+    dev = _chk("triplets", rowptr, col, src_type)
+    _i32("triplets", rowptr, col, src_type)
+    n_rows = rowptr.numel() - 1
+    with torch.cuda.device(dev):
+        counts = torch.empty(n_rows, dtype=torch.int64, device=dev)
+        st = _stream(dev)
+        _lib.check(lib.hn_triplets_count(_ptr(rowptr), n_rows, _ptr(col), _ptr(src_type), type_a, type_c, _ptr(counts), st),
+                   "hn_triplets_count")
+        trip_ptr = torch.zeros(n_rows + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(counts, 0, out=trip_ptr[1:])
+        total = int(trip_ptr[-1].item())
+        e1 = torch.empty(total, dtype=torch.int32, device=dev)
+        e2 = torch.empty(total, dtype=torch.int32, device=dev)
+        if total > 0:
+            _lib.check(lib.hn_triplets_fill(_ptr(rowptr), n_rows, _ptr(col), _ptr(src_type), type_a, type_c, _ptr(trip_ptr),
+                                            _ptr(e1), _ptr(e2), st), "hn_triplets_fill")
+    return trip_ptr, e1, e2
+
+
+def triplet_dots(m_vec: Tensor, trip_ptr: Tensor, e1: Tensor, e2: Tensor) -> Tensor:
+    lib = _lib.load()
+    dev = _chk("triplet_dots", m_vec, trip_ptr, e1, e2)
+    _f32("triplet_dots", m_vec)
+    F = m_vec.size(-1)
+    n_rows = trip_ptr.numel() - 1
+    out = torch.empty((n_rows, F), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.hn_triplet_dots(_ptr(m_vec), F, _ptr(trip_ptr), _ptr(e1), _ptr(e2), n_rows, _ptr(out), _stream(dev)),
+                   "hn_triplet_dots")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------
+# geometry
+# ----------------------------------------------------------------------------------------------------
+def edge_geom_fwd(pos: Tensor, cell: Optional[Tensor], g) -> Tensor:
+    lib = _lib.load()
+    dev = _chk("edge_geom_fwd", pos, cell)
+    _f32("edge_geom_fwd", pos, cell)
+    geom = torch.empty((g.n_edges, 4), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.hn_edge_geom_fwd(_ptr(pos), _ptr(cell), _ptr(g.atom_graph), _ptr(g.edge_row), g.rows_per_atom,
+                                        _ptr(g.col), _ptr(g.shift if cell is not None else None), float(g.sign),
+                                        g.n_edges, _ptr(geom), _stream(dev)), "hn_edge_geom_fwd")
+    return geom
+
+
+def edge_geom_bwd(geom: Tensor, g_geom: Tensor, g, want_cell: bool):
+    """``g_geom`` is ``[n_parts, E, 4]``; returns ``grad_pos [N,3]`` and the per-atom virial partial ``[N,9]``."""
+    lib = _lib.load()
+    dev = _chk("edge_geom_bwd", geom, g_geom)
+    _f32("edge_geom_bwd", geom, g_geom)
+    n_parts = g_geom.size(0) if g_geom.dim() == 3 else 1
+    grad_pos = torch.empty((g.n_atoms, 3), dtype=torch.float32, device=dev)
+    cellw = torch.empty((g.n_atoms, 9), dtype=torch.float32, device=dev) if want_cell else None
+    with torch.cuda.device(dev):
+        _lib.check(lib.hn_edge_geom_bwd(_ptr(geom), _ptr(g_geom), n_parts, _ptr(g.shift), _ptr(g.rowptr), g.rows_per_atom,
+                                        _ptr(g.t_rowptr), _ptr(g.t_eid), float(g.sign), g.n_atoms, g.n_edges,
+                                        _ptr(grad_pos), _ptr(cellw), _stream(dev)), "hn_edge_geom_bwd")
+    return grad_pos, cellw
+
+
+# ----------------------------------------------------------------------------------------------------
+# fused PaiNN edge kernels
+# ----------------------------------------------------------------------------------------------------
+def edge_params(g, n_modules: int, hidden: int, num_rbf: int, env_p: int, rc: float, coeff: float) -> EdgeParams:
+    return EdgeParams(g.n_atoms, g.n_rows, n_modules, hidden, num_rbf, env_p, 1.0 / rc, coeff)
+
+
+def edge_num_slices(hidden: int) -> int:
+    n = int(_lib.load().hn_painn_edge_num_slices(hidden))
+    if n <= 0:
+        raise RuntimeError("hermnet_b200: hidden_channels must be a multiple of 32 for the fused edge kernels")
+    return n
+
+
+def painn_edge_fwd(p: EdgeParams, xh, vec, geom, g, Wt, bias, offset):
+    lib = _lib.load()
+    dev = _chk("painn_edge_fwd", xh, vec, geom, Wt, bias, offset)
+    _f32("painn_edge_fwd", xh, vec, geom, Wt, bias, offset)
+    F = p.hidden
+    dx = torch.empty((p.n_rows, F), dtype=torch.float32, device=dev)
+    dvec = torch.empty((p.n_rows, 3, F), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.hn_painn_edge_fwd(ctypes.byref(p), _ptr(xh), _ptr(vec), _ptr(geom), _ptr(g.rowptr), _ptr(g.col),
+                                         _ptr(g.row_mod), _ptr(g.row_xoff), _ptr(Wt), _ptr(bias), _ptr(offset), _ptr(dx), _ptr(dvec),
+                                         _stream(dev)), "hn_painn_edge_fwd")
+    return dx, dvec
+
+
+def painn_edge_bwd_dst(p: EdgeParams, xh, vec, geom, g, Wt, bias, offset, g_dx, g_dvec):
+    lib = _lib.load()
+    dev = _chk("painn_edge_bwd_dst", xh, vec, geom, Wt, bias, offset, g_dx, g_dvec)
+    _f32("painn_edge_bwd_dst", xh, vec, geom, Wt, bias, offset, g_dx, g_dvec)
+    g_geom = torch.empty((edge_num_slices(p.hidden), g.n_edges, 4), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.hn_painn_edge_bwd_dst(ctypes.byref(p), _ptr(xh), _ptr(vec), _ptr(geom), _ptr(g.rowptr), _ptr(g.col),
+                                             _ptr(g.row_mod), _ptr(g.row_xoff), _ptr(Wt), _ptr(bias), _ptr(offset), _ptr(g_dx),
+                                             _ptr(g_dvec), _ptr(g_geom), g.n_edges, _stream(dev)), "hn_painn_edge_bwd_dst")
+    return g_geom
+
+
+def painn_edge_bwd_src(p: EdgeParams, xh, vec, geom, g, Wt, bias, offset, g_dx, g_dvec):
+    lib = _lib.load()
+    dev = _chk("painn_edge_bwd_src", xh, vec, geom, Wt, bias, offset, g_dx, g_dvec)
+    _f32("painn_edge_bwd_src", xh, vec, geom, Wt, bias, offset, g_dx, g_dvec)
+    grad_xh = torch.zeros_like(xh)
+    grad_vec = torch.empty_like(vec)
+    with torch.cuda.device(dev):
+        _lib.check(lib.hn_painn_edge_bwd_src(ctypes.byref(p), _ptr(xh), _ptr(vec), _ptr(geom), _ptr(g.t_rowptr),
+                                             _ptr(g.t_eid), _ptr(g.edge_row), _ptr(g.row_mod), _ptr(g.row_xoff), _ptr(Wt), _ptr(bias),
+                                             _ptr(offset), _ptr(g_dx), _ptr(g_dvec), _ptr(grad_xh), _ptr(grad_vec),
+                                             _stream(dev)), "hn_painn_edge_bwd_src")
+    return grad_xh, grad_vec
+
+
+def painn_edge_bwd_w(p: EdgeParams, xh, vec, geom, g, offset, g_dx, g_dvec):
+    """Gradients of the filter projection: ``gWt [M,K,3F]``, ``gb [M,3F]`` (partials reduced in fixed order)."""
+    lib = _lib.load()
+    dev = _chk("painn_edge_bwd_w", xh, vec, geom, offset, g_dx, g_dvec)
+    _f32("painn_edge_bwd_w", xh, vec, geom, offset, g_dx, g_dvec)
+    M, K, F3 = p.n_modules, p.num_rbf, 3 * p.hidden
+    n_chunks = max(1, min(p.n_rows, (2 * max(sm_count(), 1)) // max(M, 1)))
+    gW = torch.empty((n_chunks, M, K, F3), dtype=torch.float32, device=dev)
+    gb = torch.empty((n_chunks, M, F3), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.hn_painn_edge_bwd_w(ctypes.byref(p), _ptr(xh), _ptr(vec), _ptr(geom), _ptr(g.rowptr), _ptr(g.col),
+                                           _ptr(g.row_mod), _ptr(g.row_xoff), _ptr(offset), _ptr(g_dx), _ptr(g_dvec), _ptr(gW), _ptr(gb),
+                                           n_chunks, _stream(dev)), "hn_painn_edge_bwd_w")
+    return gW.sum(0), gb.sum(0)
+
+
+# ----------------------------------------------------------------------------------------------------
+# gather / segmented sum
+# ----------------------------------------------------------------------------------------------------
+def gather_rows(X: Tensor, idx: Tensor) -> Tensor:
+    lib = _lib.load()
+    dev = _chk("gather_rows", X, idx)
+    _f32("gather_rows", X)
+    _i32("gather_rows", idx)
+    C = X.size(1)
+    out = torch.empty((idx.numel(), C), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.hn_gather_rows(_ptr(X), _ptr(idx), idx.numel(), C, _ptr(out), _stream(dev)), "hn_gather_rows")
+    return out
+
+
+def segment_sum(Y: Tensor, rowptr: Tensor, perm: Optional[Tensor], n_rows: int) -> Tensor:
+    lib = _lib.load()
+    dev = _chk("segment_sum", Y, rowptr, perm)
+    _f32("segment_sum", Y)
+    _i32("segment_sum", rowptr, perm)
+    C = Y.size(1)
+    out = torch.empty((n_rows, C), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.hn_segment_sum(_ptr(Y), _ptr(rowptr), _ptr(perm), n_rows, C, _ptr(out), _stream(dev)),
+                   "hn_segment_sum")
+    return out

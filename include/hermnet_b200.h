@@ -1,0 +1,177 @@
+/* hermnet_b200 -- C ABI of the B200-native HermNet message-passing hot path.
+ *
+ * The reference (thu-wangz17/HermNet) has no FFI: its hot path is a chain of implicit PyTorch /
+ * PyG / torch_scatter / torch_cluster / ASE library calls.  Each entry point below names the
+ * reference call site(s) it replaces (paths relative to /root/reference).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch types.  Every pointer is a DEVICE pointer on the
+ *     current CUDA device unless stated otherwise; the caller owns every buffer (outputs, scratch).
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises.
+ *   - return value: 0 = ok, non-zero = error; `hn_last_error()` gives a thread-local message.
+ *   - variable-size outputs use two phases (count -> caller scans/allocates -> fill).
+ *   - indices are int32 (E < 2^31); triplet offsets are int64.
+ *   - float data is fp32; the neighbour test runs in fp64 (see hn_radius_graph_*).
+ *
+ * Graph layout ("row CSR")
+ *   A *row* is one segment of the segmented reduction: (destination atom [, module slot]).
+ *   rows_per_atom is constant: row r belongs to atom r / rows_per_atom.
+ *     rowptr[R+1], col[E] (source atom of each row-edge), shift[E][4] (int8 Sx,Sy,Sz,0),
+ *     row_mod[R] (module / weight-set id of the row, -1 = inactive row).
+ *   The transposed view (grouped by source atom) is t_rowptr[N+1], t_eid[E] (row-edge ids),
+ *   edge_row[E] (row of each row-edge).
+ */
+#ifndef HERMNET_B200_H
+#define HERMNET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HN_ABI_VERSION 1
+
+int hn_abi_version(void);
+const char *hn_last_error(void);
+/* number of SMs of the current device (grid sizing), <0 on error */
+int hn_device_sm_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Radius graph: cell-list neighbour search producing a centre-sorted CSR.
+ * Replaces HermNet/data.py:14-24 `neighbor_search` = ase.neighborlist.primitive_neighbor_list
+ * (periodic, data.py:19-21) / torch_cluster radius_graph (non-periodic, data.py:16).
+ *
+ * Row c*n_groups+g lists every (j, S) with group[j]==g and
+ *     || pos_j - pos_c + S.cell || < rc ,  not (j==c and S==0)
+ * evaluated as  sqrt(sum((double)(float)(pos_j-pos_c) + S.cell)^2) < rc  in fp64, un-fused
+ * (the ASE arithmetic).  cell==NULL: non-periodic, fp32 test d2 < rc*rc, S==0, and at most
+ * max_neighbors (>0) neighbours per centre, the smallest indices (torch_cluster CUDA semantics).
+ * Positions need not lie inside the cell.  Atoms of a graph are contiguous: graph_ptr[B+1].
+ * `workspace` (hn_radius_graph_workspace_bytes) carries the cell list from count to fill.
+ * Entry order inside a row is deterministic (cell-traversal order).
+ * ------------------------------------------------------------------------------------------- */
+int64_t hn_radius_graph_workspace_bytes(int64_t n_atoms, int32_t n_graphs);
+int hn_radius_graph_count(const float *pos, int64_t n_atoms, const float *cell /*[B,3,3] or NULL*/,
+                          const int32_t *graph_ptr, int32_t n_graphs, double rc,
+                          const int32_t *group /*[N] or NULL*/, int32_t n_groups, int32_t max_neighbors,
+                          int32_t *counts /*[N*n_groups]*/, void *workspace, int64_t workspace_bytes,
+                          void *stream);
+int hn_radius_graph_fill(const float *pos, int64_t n_atoms, const float *cell, const int32_t *graph_ptr,
+                         int32_t n_graphs, double rc, const int32_t *group, int32_t n_groups,
+                         int32_t max_neighbors, const int32_t *rowptr /*[N*n_groups+1]*/,
+                         int32_t *col /*[E]*/, int8_t *shift /*[E,4]*/, void *workspace,
+                         int64_t workspace_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Stable counting sort of edge ids by an integer key: order[] lists ids grouped by key ascending,
+ * original order inside a key; rowptr[n_keys+1].  Used for (a) COO -> row CSR of a user-supplied
+ * edge_index (replaces the per-atom `torch.where` scans of HermNet/utils.py:11-24 `in_subgraph`),
+ * (b) the transposed (source-major) view needed by the backward pass.
+ * ------------------------------------------------------------------------------------------- */
+int64_t hn_sort_by_key_workspace_bytes(int64_t n, int32_t n_keys);
+int hn_sort_by_key(const int32_t *keys, int64_t n, int32_t n_keys, int32_t *rowptr, int32_t *order,
+                   void *workspace, int64_t workspace_bytes, void *stream);
+/* edge_row[e] = r for rowptr[r] <= e < rowptr[r+1] */
+int hn_expand_rowptr(const int32_t *rowptr, int32_t n_rows, int32_t *edge_row, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Canonical ordered triplets (j,i,k) over row-edge ids (HTNet -- not in the
+ * reference, HermNet/hermnet.py:155-157 raises): all (e1,e2), e1 != e2, in the same row, sorted
+ * by (row, e1, e2).  Typed variant: src_type[col[e1]]==type_a and src_type[col[e2]]==type_c
+ * (pass src_type=NULL for untyped).
+ * ------------------------------------------------------------------------------------------- */
+int hn_triplets_count(const int32_t *rowptr, int32_t n_rows, const int32_t *col, const int32_t *src_type,
+                      int32_t type_a, int32_t type_c, int64_t *counts /*[R]*/, void *stream);
+int hn_triplets_fill(const int32_t *rowptr, int32_t n_rows, const int32_t *col, const int32_t *src_type,
+                     int32_t type_a, int32_t type_c, const int64_t *trip_ptr /*[R+1]*/,
+                     int32_t *e1 /*[T]*/, int32_t *e2 /*[T]*/, void *stream);
+/* dots[r][f] = sum over triplets (e1,e2) of row r of sum_k m_vec[e1][k][f]*m_vec[e2][k][f] */
+int hn_triplet_dots(const float *m_vec /*[E,3,F]*/, int32_t F, const int64_t *trip_ptr, const int32_t *e1,
+                    const int32_t *e2, int32_t n_rows, float *dots /*[R,F]*/, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Edge geometry.  Replaces HVNet.with_edge, HermNet/hermnet.py:133-152:
+ *   D = pos[col[e]] - pos[atom(row(e))] + sign * S_e . cell[graph[col[e]]]   (sign=+1: reference
+ *   quirk F5, -1: physical);  d = |D|, d <= 1e-6 -> 1e-6;  u = D/d.   geom[e] = (ux,uy,uz,d).
+ * Backward: g_geom[n_parts][E] = (dL/dux, dL/duy, dL/duz, dL/dd), summed over parts, gives
+ *   grad_pos[N,3] (segmented sums over the row CSR and its transpose -- no atomics) and, if
+ *   cellw != NULL, the per-atom virial partial cellw[i][a][b] = sign * sum_{e in rows(i)} S_e[a]*gD_e[b].
+ * ------------------------------------------------------------------------------------------- */
+int hn_edge_geom_fwd(const float *pos, const float *cell, const int32_t *atom_graph, const int32_t *edge_row,
+                     int32_t rows_per_atom, const int32_t *col, const int8_t *shift, float sign, int64_t n_edges,
+                     float *geom /*[E,4]*/, void *stream);
+int hn_edge_geom_bwd(const float *geom, const float *g_geom, int32_t n_parts, const int8_t *shift,
+                     const int32_t *rowptr, int32_t rows_per_atom, const int32_t *t_rowptr, const int32_t *t_eid,
+                     float sign, int64_t n_atoms, int64_t n_edges, float *grad_pos /*[N,3]*/,
+                     float *cellw /*[N,9] or NULL*/, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused PaiNN edge kernel.  Replaces, per layer and per sub-network, HermNet/rmnet.py:55-73
+ * (rbf_proj, propagate/message, scatter aggregate), rmnet.py:168-193 (Gaussian RBF x polynomial
+ * envelope) and the sub-graph regrouping of HermNet/utils.py:11-24 / hermnet.py:51-61:
+ *   phi_e = W[m] . (env(d/rc) * gauss_k(d/rc)) + b[m]                       (3F)
+ *   dx[r]      = sum_e  xh[m][s][0:F]  * phi_e[0:F]
+ *   dvec[r][k] = sum_e (vec[s][k] * xh[m][s][F:2F]*phi_e[F:2F]/sqrt(3) + xh[m][s][2F:3F]*phi_e[2F:3F]*u_e[k]) / sqrt(F)
+ * with m = row_mod[r], s = col[e]; segmented reduction per row, warp shuffles, no global atomics.
+ * xh is ONE flat fp32 buffer holding the projected source features of every sub-network compactly;
+ * row r reads source s at row (row_xoff[r] + s) of that [rows][3F] buffer (int64 row offsets; for a dense
+ * [M][N][3F] layout row_xoff[r] = m*N).  Wt is rbf_proj.weight transposed: [M][K][3F].  gauss_k uses the `offset` buffer (K values,
+ * linspace(0,1,K)) and coeff = -0.5/(offset[1]-offset[0])^2; F % 32 == 0.
+ * bwd_dst (row-major pass): g_geom[n_slices][E] = per-edge (dL/du, dL/dd).
+ * bwd_src (source-major pass over the transpose): grad_xh (same flat layout as xh; must be zero-filled
+ *   by the caller) and grad_vec[N][3][F].
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t n_atoms;      /* N: rows of vec / of each xh[m] */
+    int32_t n_rows;       /* R */
+    int32_t n_modules;    /* M */
+    int32_t hidden;       /* F */
+    int32_t num_rbf;      /* K */
+    int32_t env_p;        /* polynomial envelope exponent */
+    float inv_rc;         /* 1/cutoff */
+    float coeff;          /* Gaussian coefficient */
+} hn_edge_params;
+
+int32_t hn_painn_edge_num_slices(int32_t hidden);
+int hn_painn_edge_fwd(const hn_edge_params *p, const float *xh, const float *vec, const float *geom,
+                      const int32_t *rowptr, const int32_t *col, const int32_t *row_mod, const int64_t *row_xoff,
+                      const float *Wt, const float *bias, const float *offset, float *dx /*[R,F]*/,
+                      float *dvec /*[R,3,F]*/, void *stream);
+int hn_painn_edge_bwd_dst(const hn_edge_params *p, const float *xh, const float *vec, const float *geom,
+                          const int32_t *rowptr, const int32_t *col, const int32_t *row_mod, const int64_t *row_xoff,
+                          const float *Wt, const float *bias, const float *offset, const float *g_dx,
+                          const float *g_dvec, float *g_geom /*[n_slices,E,4]*/, int64_t n_edges, void *stream);
+int hn_painn_edge_bwd_src(const hn_edge_params *p, const float *xh, const float *vec, const float *geom,
+                          const int32_t *t_rowptr, const int32_t *t_eid, const int32_t *edge_row,
+                          const int32_t *row_mod, const int64_t *row_xoff, const float *Wt, const float *bias,
+                          const float *offset, const float *g_dx, const float *g_dvec, float *grad_xh /*zeroed*/,
+                          float *grad_vec /*[N,3,F]*/, void *stream);
+
+/* Filter-weight gradient of the fused path (autograd of nn.Linear rbf_proj, rmnet.py:45,55):
+ *   gW_part[chunk][m][k][c] / gb_part[chunk][m][c] hold per-row-chunk partial sums of
+ *   gW[m][k][c] = sum_e env*gauss_k(d_e) * dL/dphi_e[c],  gb[m][c] = sum_e dL/dphi_e[c];
+ *   the caller adds the n_chunks partials in fixed order (deterministic). */
+int hn_painn_edge_bwd_w(const hn_edge_params *p, const float *xh, const float *vec, const float *geom,
+                        const int32_t *rowptr, const int32_t *col, const int32_t *row_mod, const int64_t *row_xoff,
+                        const float *offset, const float *g_dx, const float *g_dvec,
+                        float *gW_part /*[n_chunks,M,K,3F]*/, float *gb_part /*[n_chunks,M,3F]*/, int32_t n_chunks,
+                        void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Row gather / segmented sum -- mutually adjoint linear primitives used by the differentiable
+ * (double-backward, training) formulation.  Replace PyG's index_select gathers (rmnet.py:58) and
+ * torch_scatter.scatter's atomicAdd (rmnet.py:71-72, hermnet.py:130) with deterministic kernels.
+ *   gather:       out[e][:] = X[idx[e]][:]
+ *   segment_sum:  out[r][:] = sum_{q in [rowptr[r],rowptr[r+1])} Y[perm ? perm[q] : q][:]
+ * Also used for halo pack (gather) / reverse halo accumulation (segment_sum) in the domain-
+ * decomposed path.
+ * ------------------------------------------------------------------------------------------- */
+int hn_gather_rows(const float *X, const int32_t *idx, int64_t n_out, int32_t C, float *out, void *stream);
+int hn_segment_sum(const float *Y, const int32_t *rowptr, const int32_t *perm, int32_t n_rows, int32_t C,
+                   float *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HERMNET_B200_H */

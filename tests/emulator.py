@@ -1,0 +1,247 @@
+"""CPU emulation of ``hermnet_b200.ops`` for the ``-m "not gpu"`` suite (TEST INFRASTRUCTURE).
+
+The product has no CPU path.  To exercise the HOST logic (graph building, row layouts, autograd wiring, model
+classes, DDP / halo plumbing under gloo) without a GPU, ``install(monkeypatch)`` swaps every function of
+``hermnet_b200.ops`` for a torch-CPU function with the same contract.  The emulated edge / geometry backward
+functions follow the formulas of the CUDA kernels (csrc/hn_edge.cu, hn_geom.cu) line by line -- including the
+16-wide Gaussian band -- so that the maths of the hand-written backward is checked against autograd of the
+oracle on the CPU; the kernels themselves are checked on the GPU by the ``-m gpu`` tests.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from hermnet_b200 import ops
+from hermnet_b200._lib import EdgeParams
+from oracle import neighbor_oracle as NO
+
+
+def _rows(rowptr):
+    lens = (rowptr[1:] - rowptr[:-1]).long()
+    return torch.repeat_interleave(torch.arange(lens.numel()), lens)
+
+
+def radius_graph(pos, cell, graph_ptr, rc, group=None, n_groups=1, max_neighbors=0):
+    pos_np = pos.detach().numpy().astype(np.float32)
+    gp = graph_ptr.tolist()
+    rows = []
+    for g in range(len(gp) - 1):
+        a0, a1 = gp[g], gp[g + 1]
+        if cell is None:
+            ei = NO.radius_graph_nonpbc(pos_np[a0:a1], rc, max_neighbors if max_neighbors > 0 else 10 ** 9)
+            i, j, S = ei[1], ei[0], np.zeros((ei.shape[1], 3), np.int64)
+        else:
+            i, j, S = NO.neighbor_list_pbc(pos_np[a0:a1], cell[g].numpy(), rc)
+        rows.append(np.concatenate([(i + a0)[:, None], (j + a0)[:, None], S], 1))
+    allr = np.concatenate(rows, 0) if rows else np.zeros((0, 5), np.int64)
+    grp = np.zeros(len(allr), np.int64) if group is None else group.numpy()[allr[:, 1]]
+    key = allr[:, 0] * n_groups + grp
+    order = np.lexsort((allr[:, 4], allr[:, 3], allr[:, 2], allr[:, 1], key))
+    allr, key = allr[order], key[order]
+    n = pos.size(0)
+    counts = np.bincount(key, minlength=n * n_groups)
+    rowptr = torch.zeros(n * n_groups + 1, dtype=torch.int32)
+    rowptr[1:] = torch.from_numpy(np.cumsum(counts)).to(torch.int32)
+    col = torch.from_numpy(allr[:, 1]).to(torch.int32)
+    shift = torch.zeros((len(allr), 4), dtype=torch.int8)
+    shift[:, :3] = torch.from_numpy(allr[:, 2:5]).to(torch.int8)
+    return rowptr, col, shift
+
+
+def sort_by_key(keys, n_keys):
+    order = torch.sort(keys.long(), stable=True).indices
+    counts = torch.bincount(keys.long(), minlength=n_keys)
+    rowptr = torch.zeros(n_keys + 1, dtype=torch.int32)
+    rowptr[1:] = torch.cumsum(counts, 0).to(torch.int32)
+    return rowptr, order.to(torch.int32)
+
+
+def expand_rowptr(rowptr, n_edges):
+    return _rows(rowptr).to(torch.int32)
+
+
+def triplets(rowptr, col, src_type=None, type_a=-1, type_c=-1):
+    rows = NO.triplets_bruteforce(rowptr.numpy(), col.numpy(), None if src_type is None else src_type.numpy(),
+                                  None if type_a < 0 else type_a, None if type_c < 0 else type_c)
+    n_rows = rowptr.numel() - 1
+    counts = np.bincount(rows[:, 1], minlength=n_rows) if len(rows) else np.zeros(n_rows, np.int64)
+    # row of a triplet = row of e1 (rows may be (atom, slot) rows: recover from e1)
+    er = _rows(rowptr).numpy()
+    counts = np.bincount(er[rows[:, 3]], minlength=n_rows) if len(rows) else np.zeros(n_rows, np.int64)
+    tp = torch.zeros(n_rows + 1, dtype=torch.int64)
+    tp[1:] = torch.from_numpy(np.cumsum(counts))
+    return tp, torch.from_numpy(rows[:, 3]).to(torch.int32), torch.from_numpy(rows[:, 4]).to(torch.int32)
+
+
+def triplet_dots(m_vec, trip_ptr, e1, e2):
+    n_rows = trip_ptr.numel() - 1
+    out = torch.zeros((n_rows, m_vec.size(-1)), dtype=m_vec.dtype)
+    row = _rows(trip_ptr)
+    out.index_add_(0, row, (m_vec[e1.long()] * m_vec[e2.long()]).sum(1))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+def _grad_D(geom, g_geom):
+    t = g_geom.sum(0) if g_geom.dim() == 3 else g_geom
+    u, d = geom[:, :3], geom[:, 3:4]
+    clamped = (d == 1.0e-6)
+    dot = (t[:, :3] * u).sum(1, keepdim=True)
+    free = t[:, 3:4] * u + (t[:, :3] - dot * u) / d
+    return torch.where(clamped, t[:, :3] / d, free)
+
+
+def edge_geom_fwd(pos, cell, g):
+    s, r = g.col.long(), torch.div(g.edge_row.long(), g.rows_per_atom, rounding_mode="floor")
+    D = pos[s] - pos[r]
+    if cell is not None:
+        S = g.shift[:, :3].to(pos.dtype) * g.sign
+        D = D + torch.einsum("ni,nij->nj", S, cell[g.atom_graph[s].long()])
+    d = D.norm(dim=-1)
+    d = torch.where(d <= 1.0e-6, torch.full_like(d, 1.0e-6), d)
+    return torch.cat([D / d[:, None], d[:, None]], 1).contiguous()
+
+
+def edge_geom_bwd(geom, g_geom, g, want_cell):
+    gD = _grad_D(geom, g_geom)
+    s, r = g.col.long(), torch.div(g.edge_row.long(), g.rows_per_atom, rounding_mode="floor")
+    grad_pos = torch.zeros((g.n_atoms, 3), dtype=geom.dtype)
+    grad_pos.index_add_(0, s, gD)
+    grad_pos.index_add_(0, r, -gD)
+    cellw = None
+    if want_cell:
+        S = g.shift[:, :3].to(geom.dtype) * g.sign
+        cellw = torch.zeros((g.n_atoms, 9), dtype=geom.dtype)
+        cellw.index_add_(0, r, (S[:, :, None] * gD[:, None, :]).reshape(-1, 9))
+    return grad_pos, cellw
+
+
+def edge_params(g, n_modules, hidden, num_rbf, env_p, rc, coeff):
+    return EdgeParams(g.n_atoms, g.n_rows, n_modules, hidden, num_rbf, env_p, 1.0 / rc, coeff)
+
+
+def edge_num_slices(hidden):
+    return 1
+
+
+def _band(p, geom, offset, deriv=False):
+    """val[e, k] (and dval) with the kernel's 16-wide band; zeros outside the band / beyond the cutoff."""
+    K = p.num_rbf
+    u = geom[:, 3] * p.inv_rc
+    nb = min(16, K)
+    kc = torch.floor(u * (K - 1)).long()
+    k0 = (kc - 7).clamp(min=0).clamp(max=K - nb)
+    k = torch.arange(K)[None, :]
+    inband = (k >= k0[:, None]) & (k < k0[:, None] + nb) & (u < 1)[:, None]
+    pp = p.env_p
+    a, b, c = -0.5 * (pp + 1) * (pp + 2), float(pp * (pp + 2)), -0.5 * pp * (pp + 1)
+    env = 1 + a * u ** pp + b * u ** (pp + 1) + c * u ** (pp + 2)
+    diff = u[:, None] - offset[None, :]
+    gk = torch.exp(p.coeff * diff * diff)
+    val = torch.where(inband, env[:, None] * gk, torch.zeros_like(gk))
+    if not deriv:
+        return val
+    denv = a * pp * u ** (pp - 1) + b * (pp + 1) * u ** pp + c * (pp + 2) * u ** (pp + 1)
+    dval = (denv[:, None] * gk + env[:, None] * gk * (2 * p.coeff * diff)) * p.inv_rc
+    return val, torch.where(inband, dval, torch.zeros_like(dval))
+
+
+def _edge_common(p, xh, vec, geom, g, Wt, bias, offset, deriv=False):
+    F = p.hidden
+    row = g.edge_row.long()
+    m = g.row_mod.long()[row]
+    live = m >= 0
+    mm = m.clamp(min=0)
+    s = g.col.long()
+    P = xh[(g.row_xoff[row] + s).clamp(min=0)]
+    V = vec[s]
+    band = _band(p, geom, offset, deriv)
+    val = band[0] if deriv else band
+    phi = torch.einsum("ek,ekc->ec", val, Wt[mm]) + bias[mm]
+    dphi = torch.einsum("ek,ekc->ec", band[1], Wt[mm]) if deriv else None
+    return F, row, mm, live, s, P, V, val, phi, dphi
+
+
+def painn_edge_fwd(p, xh, vec, geom, g, Wt, bias, offset):
+    F, row, mm, live, s, P, V, val, phi, _ = _edge_common(p, xh, vec, geom, g, Wt, bias, offset)
+    c1, c2 = 1 / math.sqrt(3.0 * F), 1 / math.sqrt(F)
+    a, b, c = torch.split(P * phi, F, dim=-1)
+    mv = V * (b * c1)[:, None, :] + (c * c2)[:, None, :] * geom[:, :3, None]
+    lv = live.to(xh.dtype)
+    dx = torch.zeros((p.n_rows, F), dtype=xh.dtype).index_add_(0, row, a * lv[:, None])
+    dvec = torch.zeros((p.n_rows, 3, F), dtype=xh.dtype).index_add_(0, row, mv * lv[:, None, None])
+    return dx, dvec
+
+
+def _t_terms(p, V, geom, g_dvec, row, F):
+    c1, c2 = 1 / math.sqrt(3.0 * F), 1 / math.sqrt(F)
+    gv = g_dvec[row]                                    # [E,3,F]
+    tb = (gv * V).sum(1) * c1
+    tc = (gv * geom[:, :3, None]).sum(1) * c2
+    return gv, tb, tc, c1, c2
+
+
+def painn_edge_bwd_dst(p, xh, vec, geom, g, Wt, bias, offset, g_dx, g_dvec):
+    F, row, mm, live, s, P, V, val, phi, dphi = _edge_common(p, xh, vec, geom, g, Wt, bias, offset, deriv=True)
+    gv, tb, tc, c1, c2 = _t_terms(p, V, geom, g_dvec, row, F)
+    Pa, Pb, Pc = torch.split(P, F, dim=-1)
+    da, db, dc = torch.split(dphi, F, dim=-1)
+    gd = (g_dx[row] * Pa * da + tb * Pb * db + tc * Pc * dc).sum(1)
+    cphi = Pc * phi[:, 2 * F:] * c2
+    gu = (gv * cphi[:, None, :]).sum(2)
+    out = torch.cat([gu, gd[:, None]], 1) * live.to(xh.dtype)[:, None]
+    return out.view(1, -1, 4).contiguous()
+
+
+def painn_edge_bwd_src(p, xh, vec, geom, g, Wt, bias, offset, g_dx, g_dvec):
+    F, row, mm, live, s, P, V, val, phi, _ = _edge_common(p, xh, vec, geom, g, Wt, bias, offset)
+    gv, tb, tc, c1, c2 = _t_terms(p, V, geom, g_dvec, row, F)
+    fa, fb, fc = torch.split(phi, F, dim=-1)
+    lv = live.to(xh.dtype)[:, None]
+    gP = torch.cat([g_dx[row] * fa, tb * fb, tc * fc], 1) * lv
+    grad_xh = torch.zeros_like(xh).index_add_(0, (g.row_xoff[row] + s).clamp(min=0), gP)
+    bphi = P[:, F:2 * F] * fb * c1 * lv
+    grad_vec = torch.zeros_like(vec).index_add_(0, s, gv * bphi[:, None, :])
+    return grad_xh, grad_vec
+
+
+def painn_edge_bwd_w(p, xh, vec, geom, g, offset, g_dx, g_dvec):
+    F = p.hidden
+    row = g.edge_row.long()
+    m = g.row_mod.long()[row]
+    live = (m >= 0).to(xh.dtype)[:, None]
+    mm = m.clamp(min=0)
+    s = g.col.long()
+    P = xh[(g.row_xoff[row] + s).clamp(min=0)]
+    V = vec[s]
+    gv, tb, tc, c1, c2 = _t_terms(p, V, geom, g_dvec, row, F)
+    gphi = torch.cat([g_dx[row] * P[:, :F], tb * P[:, F:2 * F], tc * P[:, 2 * F:]], 1) * live
+    val = _band(p, geom, offset)
+    gW = torch.zeros((p.n_modules, p.num_rbf, 3 * F), dtype=xh.dtype)
+    gW.index_add_(0, mm, val[:, :, None] * gphi[:, None, :])
+    gb = torch.zeros((p.n_modules, 3 * F), dtype=xh.dtype).index_add_(0, mm, gphi)
+    return gW, gb
+
+
+def gather_rows(X, idx):
+    return X[idx.long()].contiguous()
+
+
+def segment_sum(Y, rowptr, perm, n_rows):
+    items = torch.arange(Y.size(0)) if perm is None else perm.long()
+    row = _rows(rowptr)
+    return torch.zeros((n_rows, Y.size(1)), dtype=Y.dtype).index_add_(0, row, Y[items])
+
+
+def install(monkeypatch):
+    """Swap ``hermnet_b200.ops`` for the CPU emulation (pytest ``monkeypatch`` restores it afterwards)."""
+    for name in ("radius_graph", "sort_by_key", "expand_rowptr", "triplets", "triplet_dots", "edge_geom_fwd",
+                 "edge_geom_bwd", "edge_params", "edge_num_slices", "painn_edge_fwd", "painn_edge_bwd_dst",
+                 "painn_edge_bwd_src", "painn_edge_bwd_w", "gather_rows", "segment_sum"):
+        monkeypatch.setattr(ops, name, globals()[name])
+    monkeypatch.setattr(ops, "require_cuda", lambda t, what: None)
+    monkeypatch.setattr(ops, "compute_device", lambda t: t.device)
+    monkeypatch.setattr(ops, "sm_count", lambda: 148)

@@ -1,0 +1,143 @@
+"""Host-side logic over the CPU kernel emulator (tests/emulator.py): graph layouts, autograd wiring, the model
+classes, both formulations -- compared with the golden fixtures / the oracle.  No GPU needed."""
+import numpy as np
+import pytest
+import torch
+
+import hermnet_b200 as H
+from oracle import hermnet_oracle as O
+from tests import util
+
+TOL_E, TOL_F = 1e-5, 1e-4      # BASELINE.json: fp32 energy 1e-5 relative, forces 1e-4 eV/A
+
+
+@pytest.mark.parametrize("name", util.ALL_CASES)
+@pytest.mark.parametrize("path", ["fused", "composite"])
+@pytest.mark.parametrize("with_edges", [True, False])
+def test_model_matches_golden(emu, name, path, with_edges):
+    case = util.load_case(name)
+    if name == "c1_hvnet" and path == "composite" and not with_edges:
+        pytest.skip("covered by the other three combinations; keeps the CPU suite short")
+    model, _ = util.make_model(case["kind"], case["cfg"], case["seed"])
+    model.edge_path = path
+    data = util.make_data(case, with_edges=with_edges)
+    e, f, gc = util.energy_forces(model, data)
+    assert util.rel_err(e, case["energy"]) < TOL_E
+    assert float((f - case["forces"]).abs().max()) < TOL_F
+    if case["cell_grad"] is not None:
+        assert float((gc - case["cell_grad"]).abs().max()) < TOL_F * 10
+
+
+@pytest.mark.parametrize("name", ["triclinic_multi_image", "batch3_mixed", "water24_hpnet", "water24_htnet"])
+def test_parameter_gradients_fused_and_composite(emu, name):
+    """dE/dtheta from the fused backward (incl. the filter-weight kernel formula) == composite == oracle."""
+    case = util.load_case(name)
+    grads = {}
+    for path in ("fused", "composite"):
+        model, sd = util.make_model(case["kind"], case["cfg"], case["seed"])
+        model.edge_path = path
+        e = model(util.make_data(case, requires_grad=False))
+        e.sum().backward()
+        grads[path] = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+    sd_o = {k: v.clone().requires_grad_(v.is_floating_point() and "offset" not in k) for k, v in sd.items()}
+    eo = O.FORWARDS[case["kind"]](sd_o, case["cfg"], case["pos"], case["Z"], case["edge_index"], case["cell"],
+                                  case["edge_shift"], case["batch"])
+    eo.sum().backward()
+    for k, go in ((k, v.grad) for k, v in sd_o.items() if v.requires_grad and v.grad is not None):
+        scale = float(go.abs().max()) + 1e-6
+        for path in grads:
+            assert k in grads[path], (k, path)
+            assert float((grads[path][k] - go).abs().max()) < 2e-4 * scale + 1e-6, (k, path)
+
+
+@pytest.mark.parametrize("name", ["triclinic_multi_image", "water24_hpnet"])
+def test_force_loss_double_backward(emu, name):
+    """Training step of example/dist_train.py:89-99: loss on forces obtained with create_graph=True."""
+    case = util.load_case(name)
+    model, sd = util.make_model(case["kind"], case["cfg"], case["seed"])
+    model.train()
+    data = util.make_data(case)
+    e = model(data)
+    f = -torch.autograd.grad(e.sum(), data.pos, create_graph=True)[0]
+    loss = 0.2 * (e ** 2).mean() + 0.8 * (f ** 2).mean()
+    loss.backward()
+    sd_o = {k: v.clone().requires_grad_(v.is_floating_point() and "offset" not in k) for k, v in sd.items()}
+    pos = case["pos"].clone().requires_grad_(True)
+    eo = O.FORWARDS[case["kind"]](sd_o, case["cfg"], pos, case["Z"], case["edge_index"], case["cell"],
+                                  case["edge_shift"], case["batch"])
+    fo = -torch.autograd.grad(eo.sum(), pos, create_graph=True)[0]
+    (0.2 * (eo ** 2).mean() + 0.8 * (fo ** 2).mean()).backward()
+    checked = 0
+    for k, p in model.named_parameters():
+        go = sd_o[k].grad
+        if go is None:
+            continue
+        assert p.grad is not None, k
+        assert float((p.grad - go).abs().max()) < 2e-4 * (float(go.abs().max()) + 1e-6) + 1e-6, k
+        checked += 1
+    assert checked > 10
+
+
+def test_eval_mode_refuses_double_backward(emu):
+    case = util.load_case("triclinic_multi_image")
+    model, _ = util.make_model(case["kind"], case["cfg"], case["seed"])
+    data = util.make_data(case)
+    e = model(data)
+    f = torch.autograd.grad(e.sum(), data.pos, create_graph=True)[0]
+    with pytest.raises(RuntimeError):
+        (f ** 2).sum().backward()
+
+
+def test_in_subgraph_matches_reference_regrouping(emu):
+    case = util.load_case("batch3_mixed")
+    data = util.make_data(case, requires_grad=False)
+    nids = torch.where(data.atomic_number == 8)[0]
+    rel = H.in_subgraph(data, nids)
+    want = O.in_subgraph_edges_literal(data.edge_index[1], nids)
+    assert torch.equal(rel.edge_index, data.edge_index[:, want])
+    assert torch.equal(rel.edge_shift, data.edge_shift[want])
+    assert rel.pos is data.pos
+
+
+def test_neighbor_search_contract(emu):
+    case = util.load_case("triclinic_multi_image")
+    ei, es = H.neighbor_search(case["pos"], 5.0, case["cell"])
+    assert ei.dtype == torch.int64 and es.dtype == torch.float32
+    assert torch.all(ei[0][1:] >= ei[0][:-1])          # sorted by edge_index[0] like ASE's 'ijS'
+    from oracle.neighbor_oracle import canonical_edges
+    assert np.array_equal(canonical_edges(ei.numpy(), es.numpy()), case["edges"])
+    case = util.load_case("cluster_nonpbc_capped")
+    ei = H.neighbor_search(case["pos"], 5.0)
+    assert np.array_equal(canonical_edges(ei.numpy()), case["edges"])
+    assert int(torch.bincount(ei[1]).max()) == 32
+
+
+def test_batch_collation_and_intensive(emu):
+    case = util.load_case("batch3_mixed")
+    parts = []
+    for g in range(3):
+        sel = case["batch"] == g
+        d = H.Data(pos=case["pos"][sel], atomic_number=case["Z"][sel], cell=case["cell"][g:g + 1])
+        parts.append(H.transform(d, case["cfg"]["rc"]))
+    b = H.Batch.from_data_list(parts)
+    assert b.num_graphs == 3 and torch.equal(b.batch, case["batch"]) and b.cell.shape == (3, 3, 3)
+    model, sd = util.make_model(case["kind"], case["cfg"], case["seed"])
+    e = model(b)
+    assert util.rel_err(e.detach(), case["energy"]) < TOL_E
+    model_i, _ = util.make_model(case["kind"], case["cfg"], case["seed"], intensive=True)
+    ei = model_i(b)
+    counts = torch.bincount(case["batch"]).float()
+    assert torch.allclose(ei.detach() * counts, e.detach(), rtol=1e-5, atol=1e-6)
+
+
+def test_unknown_basis_raises():
+    with pytest.raises(ValueError):
+        H.HVNet(["H"], rbf={"name": "nope"})
+    with pytest.raises(ValueError):
+        H.HVNet(["H"], envelope={"name": "nope"})
+
+
+def test_cpu_input_without_emulator_fails_loudly():
+    model = H.HVNet(["H", "O"], num_layers=1, hidden_channels=32, num_rbf=16)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model(H.Data(pos=torch.zeros(3, 3), atomic_number=torch.ones(3, dtype=torch.long)))
