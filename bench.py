@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""Headline benchmark of the HermNet hot path on B200 (contract: see the task brief / DESIGN.md "Measurement").
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload C4] [--scale S]
+
+Workload (BASELINE.json configs[3], the configuration the metric "atom-steps/s (energy+forces)" is quoted on and the
+largest that fits one GPU): HVNet, 3 interactions, F=128, K=128, rc=5 A on the synthetic 1 000 000-atom Li/Al/Si/O
+periodic box, evaluated as energy + forces (forward + backward to positions).  N > 1 runs the SAME system with
+spatial domain decomposition (hermnet_b200/parallel.py): strong scaling.
+
+One JSON line on stdout (rank 0).  ``value``: graph and inputs resident in HBM, timed with CUDA events.
+``e2e``: the same metric through the public API from pinned HOST buffers -- H2D copy of positions / numbers / cell,
+neighbour-list build, forward, backward, D2H of forces + energy all inside the timed region.
+``--impl reference`` times the CPU restatement of the reference PyG path (oracle/, the reference itself cannot be
+imported without PyG / torch_scatter / ASE) on a bounded sample of the same workload with all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HBM_FALLBACK_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C4")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the box edge (debug only; 1.0 = BASELINE size)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (profiling recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+
+
+def workload(name: str, scale: float):
+    from hermnet_b200 import synthetic
+    (pos, Z, cell), cfg = synthetic.config(name, scale)
+    return pos, Z, cell, cfg
+
+
+def alg_bytes(kernel: str, N: int, E: int, T: int, F: int) -> float:
+    """Algorithmic (compulsory, each array once) bytes of one launch -- SURVEY.md 8(d), stated in DESIGN.md."""
+    xh, vec, out = 4.0 * N * 3 * F * T, 4.0 * N * 3 * F, 4.0 * N * 4 * F
+    if kernel == "painn_edge_fwd":          # xh + vec in, dx + dvec out, (col 4 + geom 16) per edge, rowptr
+        return xh + vec + out + 20.0 * E + 4.0 * (N + 1)
+    if kernel == "painn_edge_bwd_dst":      # + g_dx/g_dvec in, per-edge (dL/du, dL/dd) out
+        return xh + vec + out + 20.0 * E + 16.0 * E + 4.0 * (N + 1)
+    if kernel == "painn_edge_bwd_src":      # xh, vec, g_dx/g_dvec in; grad_xh, grad_vec out; t_eid + edge_row + geom per edge
+        return 2 * xh + 2 * vec + out + 24.0 * E + 4.0 * (N + 1)
+    return float("nan")
+
+
+# --------------------------------------------------------------------------------------------------------------
+def cpu_baseline(cfg, seconds_budget=25.0, n_side=12):
+    """Oracle (CPU restatement of the reference PyG path, vectorised sub-graph variant) on a bounded sample: a
+    ``n_side^3``-atom box with the workload's lattice / density / species / model, forward + backward to pos."""
+    from hermnet_b200 import synthetic
+    from oracle import hermnet_oracle as O
+    from oracle import neighbor_oracle as NO
+    torch.set_num_threads(os.cpu_count() or 1)
+    pos, Z, cell = synthetic.cubic_lattice(n_side, 2.3, ("Li", "Al", "Si", "O"), None, 0.10, 4)
+    mcfg = {k: v for k, v in cfg.items() if k != "kind"}
+    sd = O.make_state_dict("HVNet", mcfg, 1234)
+    t0 = time.perf_counter()
+    i, j, S = NO.neighbor_list_pbc(pos, cell, mcfg["rc"])
+    t_nl = time.perf_counter() - t0
+    ei, es = torch.from_numpy(np.stack([i, j])), torch.from_numpy(S.astype(np.float32))
+    p, z, c = torch.from_numpy(pos), torch.from_numpy(Z), torch.from_numpy(cell)[None]
+    times = []
+    t_start = time.perf_counter()
+    while len(times) < 2 or (time.perf_counter() - t_start < seconds_budget and len(times) < 6):
+        t0 = time.perf_counter()
+        O.energy_and_forces("HVNet", sd, mcfg, p, z, ei, c, es)
+        times.append(time.perf_counter() - t0)
+    t = statistics.median(times[1:]) if len(times) > 1 else times[0]
+    n = len(Z)
+    return {"value": n / t, "unit": "atom-steps/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n}-atom Li/Al/Si/O box (same lattice, density, species and HVNet L=3 F=128 K=128 rc=5 as the "
+                      f"1M-atom workload), E={ei.shape[1]}, oracle forward+backward, median of {len(times) - 1} after 1 "
+                      f"warm-up; numpy neighbour list {t_nl:.2f}s not included",
+            "seconds_per_step": t}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    _, _, _, cfg = workload(args.workload, 0.05)
+    times = []
+    base = None
+    for _ in range(max(1, args.warmup) + max(1, args.steps)):
+        base = cpu_baseline(cfg, seconds_budget=0.0, n_side=12)
+        times.append(base["seconds_per_step"])
+    times = times[max(1, args.warmup):]
+    t = sum(times) / len(times)
+    n = 12 ** 3
+    val = n / t
+    base["value"] = val
+    line = {"impl": "reference", "metric": "atom-steps/s (energy+forces)", "value": val, "unit": "atom-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C4: HVNet L=3 F=128 K=128 rc=5, Li/Al/Si/O periodic box; reference CPU path timed on a "
+                                   "1728-atom sample of it (the 1M-atom O(N*E) path does not finish on a CPU)"},
+            "cpu_baseline": base,
+            "e2e": {"value": val, "unit": "atom-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    import hermnet_b200 as H
+    from hermnet_b200 import ops
+    pos, Z, cell, cfg = workload(args.workload, args.scale)
+    N = len(Z)
+    kind = cfg.pop("kind")
+    torch.manual_seed(1234)
+    model = getattr(H, kind)(**cfg).to(dev).eval()
+    for p_ in model.parameters():          # inference: parameters frozen (the ASE plugin does the same)
+        p_.requires_grad_(False)
+    T, F = len(cfg["elems"]), cfg["hidden_channels"]
+
+    pos_h = torch.from_numpy(pos).pin_memory()
+    Z_h = torch.from_numpy(Z).pin_memory()
+    cell_h = torch.from_numpy(cell)[None].pin_memory()
+    f_h = torch.empty((N, 3), dtype=torch.float32).pin_memory()
+    e_h = torch.empty(1, dtype=torch.float32).pin_memory()
+
+    if world > 1:
+        from hermnet_b200 import parallel
+        engine = parallel.DomainDecomposition(model, dev)
+    else:
+        engine = None
+
+    # ---- resident setup ------------------------------------------------------------------------------------
+    pos_d, Z_d, cell_d = pos_h.to(dev), Z_h.to(dev), cell_h.to(dev)
+    if engine is None:
+        graph = model.build_graph(pos_d, Z_d, cell_d, None)
+        n_edges = graph.n_edges
+    else:
+        engine.build(pos_d, Z_d, cell_d)
+        n_edges = engine.global_edges
+
+    def step_resident():
+        if engine is None:
+            p = pos_d.detach().requires_grad_(True)
+            e, _, _ = model.forward_graph(p, Z_d, cell_d, graph)
+            (g,) = torch.autograd.grad(e.sum(), p)
+            return e, g
+        return engine.energy_forces(pos_d)
+
+    def step_e2e():
+        p = pos_h.to(dev, non_blocking=True)
+        z = Z_h.to(dev, non_blocking=True)
+        c = cell_h.to(dev, non_blocking=True)
+        if engine is None:
+            d = H.Data(pos=p.requires_grad_(True), atomic_number=z, cell=c)
+            e = model(d)
+            (g,) = torch.autograd.grad(e.sum(), d.pos)
+        else:
+            engine.build(p, z, c)
+            e, g = engine.energy_forces(p)
+        if rank == 0:
+            f_h.copy_(-g, non_blocking=True)
+            e_h.copy_(e.reshape(1), non_blocking=True)
+        torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.TIMERS = {}
+    ops.LAUNCHES["n"] = 0
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0.record()
+    for _ in range(args.steps):
+        step_resident()
+    t1.record()
+    barrier()
+    launches = ops.LAUNCHES["n"]
+    timers, ops.TIMERS = ops.TIMERS, None
+    ms = t0.elapsed_time(t1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms / args.steps
+    value = N * args.steps / (ms * 1e-3)
+
+    # ---- end to end from host buffers ------------------------------------------------------------------------
+    e2e_s = float("nan")
+    if args.e2e_steps > 0:
+        step_e2e()
+        barrier()
+        w0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            step_e2e()
+        barrier()
+        e2e_s = (time.perf_counter() - w0) / args.e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel device times (CUDA events recorded around every launch inside the timed region) ------------
+    kernels = {}
+    for name, evs in timers.items():
+        dur = [a.elapsed_time(b) for a, b in evs]
+        kernels[name] = {"launches": len(dur), "avg_ms": sum(dur) / len(dur), "share_of_step": sum(dur) / ms}
+    peak, peak_src = hbm_peak()
+    n_loc = N if engine is None else engine.n_owned_max
+    e_loc = n_edges if engine is None else engine.local_edges_max
+    roof = None
+    edge_k = {k: v for k, v in kernels.items() if k.startswith("painn_edge")}
+    if edge_k:
+        top = max(edge_k, key=lambda k: edge_k[k]["avg_ms"] * edge_k[k]["launches"])
+        ab = alg_bytes(top, n_loc, e_loc, T, F)
+        ach = ab / (edge_k[top]["avg_ms"] * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(top)
+        roof = {"kernel": top, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": traffic, "peak_source": peak_src, "alg_bytes_per_launch": ab,
+                "avg_launch_ms": edge_k[top]["avg_ms"]}
+        for k in edge_k:
+            kb = alg_bytes(k, n_loc, e_loc, T, F)
+            kernels[k]["alg_GBps"] = kb / (edge_k[k]["avg_ms"] * 1e-3) / 1e9
+            kernels[k]["frac_of_hbm_peak"] = kernels[k]["alg_GBps"] / peak
+
+    line = {
+        "metric": "atom-steps/s (energy+forces)", "value": value, "unit": "atom-steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {kind} L={cfg['num_layers']} F={F} K={cfg['num_rbf']} rc={cfg['rc']} on a "
+                               f"{N}-atom {'/'.join(cfg['elems'])} periodic box (E={n_edges} directed edges), energy + forces, "
+                               f"parameters frozen" + ("" if args.scale == 1.0 else f" [scale={args.scale}: NOT the BASELINE size]"),
+                   "parallelism": "single GPU" if world == 1 else f"spatial domain decomposition over {world} GPUs, per-layer halo exchange",
+                   "l2_policy": "inputs exceed L2 (feature tensors are GBs); no flush needed"},
+        "e2e": {"value": N / e2e_s, "unit": "atom-steps/s", "h2d_bytes_per_step": int(pos_h.nbytes + Z_h.nbytes + cell_h.nbytes),
+                "d2h_bytes_per_step": int(f_h.nbytes + e_h.nbytes), "ms_per_step": 1e3 * e2e_s,
+                "includes": "H2D, neighbour-list + row-CSR build, forward, backward, D2H of forces and energy"},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kernels,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(dict(cfg, kind=kind))
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

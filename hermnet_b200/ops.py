@@ -72,6 +72,30 @@ def compute_device(t: Tensor) -> torch.device:
     return torch.device("cuda", torch.cuda.current_device())
 
 
+# ---- instrumentation used by bench.py: per-kernel CUDA-event timing on the launching stream, launch counting ----
+TIMERS = None          # set to {} to collect name -> [(start_event, end_event), ...]
+LAUNCHES = {"n": 0}    # hand-written kernels launched through this module (cub passes are not counted)
+
+
+class _timed:
+    def __init__(self, name: str, dev, kernels: int = 1):
+        self.name, self.dev, self.kernels = name, dev, kernels
+
+    def __enter__(self):
+        LAUNCHES["n"] += self.kernels
+        if TIMERS is not None:
+            self.t0 = torch.cuda.Event(enable_timing=True)
+            self.t0.record(torch.cuda.current_stream(self.dev))
+        return self
+
+    def __exit__(self, *exc):
+        if TIMERS is not None:
+            t1 = torch.cuda.Event(enable_timing=True)
+            t1.record(torch.cuda.current_stream(self.dev))
+            TIMERS.setdefault(self.name, []).append((self.t0, t1))
+        return False
+
+
 def sm_count() -> int:
     return int(_lib.load().hn_device_sm_count())
 
@@ -94,6 +118,7 @@ def radius_graph(pos: Tensor, cell: Optional[Tensor], graph_ptr: Tensor, rc: flo
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         counts = torch.empty(n * n_groups, dtype=torch.int32, device=dev)
         st = _stream(dev)
+        LAUNCHES["n"] += 6
         _lib.check(lib.hn_radius_graph_count(_ptr(pos), n, _ptr(cell), _ptr(graph_ptr), n_graphs, float(rc), _ptr(group),
                                              n_groups, max_neighbors, _ptr(counts), _ptr(ws), ws_bytes, st),
                    "hn_radius_graph_count")
@@ -103,6 +128,7 @@ def radius_graph(pos: Tensor, cell: Optional[Tensor], graph_ptr: Tensor, rc: flo
         col = torch.empty(n_edges, dtype=torch.int32, device=dev)
         shift = torch.empty((n_edges, 4), dtype=torch.int8, device=dev)
         if n_edges > 0:
+            LAUNCHES["n"] += 1
             _lib.check(lib.hn_radius_graph_fill(_ptr(pos), n, _ptr(cell), _ptr(graph_ptr), n_graphs, float(rc), _ptr(group),
                                                 n_groups, max_neighbors, _ptr(rowptr), _ptr(col), _ptr(shift), _ptr(ws),
                                                 ws_bytes, st), "hn_radius_graph_fill")
@@ -120,6 +146,7 @@ def sort_by_key(keys: Tensor, n_keys: int) -> Tuple[Tensor, Tensor]:
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         rowptr = torch.empty(n_keys + 1, dtype=torch.int32, device=dev)
         order = torch.empty(n, dtype=torch.int32, device=dev)
+        LAUNCHES["n"] += 1
         _lib.check(lib.hn_sort_by_key(_ptr(keys), n, n_keys, _ptr(rowptr), _ptr(order), _ptr(ws), ws_bytes, _stream(dev)),
                    "hn_sort_by_key")
     return rowptr, order
@@ -130,7 +157,7 @@ def expand_rowptr(rowptr: Tensor, n_edges: int) -> Tensor:
     dev = _chk("expand_rowptr", rowptr)
     _i32("expand_rowptr", rowptr)
     out = torch.empty(n_edges, dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _timed("expand_rowptr", dev):
         _lib.check(lib.hn_expand_rowptr(_ptr(rowptr), rowptr.numel() - 1, _ptr(out), _stream(dev)), "hn_expand_rowptr")
     return out
 
@@ -178,7 +205,7 @@ def edge_geom_fwd(pos: Tensor, cell: Optional[Tensor], g) -> Tensor:
     dev = _chk("edge_geom_fwd", pos, cell)
     _f32("edge_geom_fwd", pos, cell)
     geom = torch.empty((g.n_edges, 4), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _timed("edge_geom_fwd", dev):
         _lib.check(lib.hn_edge_geom_fwd(_ptr(pos), _ptr(cell), _ptr(g.atom_graph), _ptr(g.edge_row), g.rows_per_atom,
                                         _ptr(g.col), _ptr(g.shift if cell is not None else None), float(g.sign),
                                         g.n_edges, _ptr(geom), _stream(dev)), "hn_edge_geom_fwd")
@@ -193,7 +220,7 @@ def edge_geom_bwd(geom: Tensor, g_geom: Tensor, g, want_cell: bool):
     n_parts = g_geom.size(0) if g_geom.dim() == 3 else 1
     grad_pos = torch.empty((g.n_atoms, 3), dtype=torch.float32, device=dev)
     cellw = torch.empty((g.n_atoms, 9), dtype=torch.float32, device=dev) if want_cell else None
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _timed("edge_geom_bwd", dev):
         _lib.check(lib.hn_edge_geom_bwd(_ptr(geom), _ptr(g_geom), n_parts, _ptr(g.shift), _ptr(g.rowptr), g.rows_per_atom,
                                         _ptr(g.t_rowptr), _ptr(g.t_eid), float(g.sign), g.n_atoms, g.n_edges,
                                         _ptr(grad_pos), _ptr(cellw), _stream(dev)), "hn_edge_geom_bwd")
@@ -221,7 +248,7 @@ def painn_edge_fwd(p: EdgeParams, xh, vec, geom, g, Wt, bias, offset):
     F = p.hidden
     dx = torch.empty((p.n_rows, F), dtype=torch.float32, device=dev)
     dvec = torch.empty((p.n_rows, 3, F), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _timed("painn_edge_fwd", dev):
         _lib.check(lib.hn_painn_edge_fwd(ctypes.byref(p), _ptr(xh), _ptr(vec), _ptr(geom), _ptr(g.rowptr), _ptr(g.col),
                                          _ptr(g.row_mod), _ptr(g.row_xoff), _ptr(Wt), _ptr(bias), _ptr(offset), _ptr(dx), _ptr(dvec),
                                          _stream(dev)), "hn_painn_edge_fwd")
@@ -233,7 +260,7 @@ def painn_edge_bwd_dst(p: EdgeParams, xh, vec, geom, g, Wt, bias, offset, g_dx, 
     dev = _chk("painn_edge_bwd_dst", xh, vec, geom, Wt, bias, offset, g_dx, g_dvec)
     _f32("painn_edge_bwd_dst", xh, vec, geom, Wt, bias, offset, g_dx, g_dvec)
     g_geom = torch.empty((edge_num_slices(p.hidden), g.n_edges, 4), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _timed("painn_edge_bwd_dst", dev):
         _lib.check(lib.hn_painn_edge_bwd_dst(ctypes.byref(p), _ptr(xh), _ptr(vec), _ptr(geom), _ptr(g.rowptr), _ptr(g.col),
                                              _ptr(g.row_mod), _ptr(g.row_xoff), _ptr(Wt), _ptr(bias), _ptr(offset), _ptr(g_dx),
                                              _ptr(g_dvec), _ptr(g_geom), g.n_edges, _stream(dev)), "hn_painn_edge_bwd_dst")
@@ -246,7 +273,7 @@ def painn_edge_bwd_src(p: EdgeParams, xh, vec, geom, g, Wt, bias, offset, g_dx, 
     _f32("painn_edge_bwd_src", xh, vec, geom, Wt, bias, offset, g_dx, g_dvec)
     grad_xh = torch.zeros_like(xh)
     grad_vec = torch.empty_like(vec)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _timed("painn_edge_bwd_src", dev):
         _lib.check(lib.hn_painn_edge_bwd_src(ctypes.byref(p), _ptr(xh), _ptr(vec), _ptr(geom), _ptr(g.t_rowptr),
                                              _ptr(g.t_eid), _ptr(g.edge_row), _ptr(g.row_mod), _ptr(g.row_xoff), _ptr(Wt), _ptr(bias),
                                              _ptr(offset), _ptr(g_dx), _ptr(g_dvec), _ptr(grad_xh), _ptr(grad_vec),
@@ -263,7 +290,7 @@ def painn_edge_bwd_w(p: EdgeParams, xh, vec, geom, g, offset, g_dx, g_dvec):
     n_chunks = max(1, min(p.n_rows, (2 * max(sm_count(), 1)) // max(M, 1)))
     gW = torch.empty((n_chunks, M, K, F3), dtype=torch.float32, device=dev)
     gb = torch.empty((n_chunks, M, F3), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _timed("painn_edge_bwd_w", dev):
         _lib.check(lib.hn_painn_edge_bwd_w(ctypes.byref(p), _ptr(xh), _ptr(vec), _ptr(geom), _ptr(g.rowptr), _ptr(g.col),
                                            _ptr(g.row_mod), _ptr(g.row_xoff), _ptr(offset), _ptr(g_dx), _ptr(g_dvec), _ptr(gW), _ptr(gb),
                                            n_chunks, _stream(dev)), "hn_painn_edge_bwd_w")
@@ -280,7 +307,7 @@ def gather_rows(X: Tensor, idx: Tensor) -> Tensor:
     _i32("gather_rows", idx)
     C = X.size(1)
     out = torch.empty((idx.numel(), C), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _timed("gather_rows", dev):
         _lib.check(lib.hn_gather_rows(_ptr(X), _ptr(idx), idx.numel(), C, _ptr(out), _stream(dev)), "hn_gather_rows")
     return out
 
@@ -292,7 +319,7 @@ def segment_sum(Y: Tensor, rowptr: Tensor, perm: Optional[Tensor], n_rows: int) 
     _i32("segment_sum", rowptr, perm)
     C = Y.size(1)
     out = torch.empty((n_rows, C), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _timed("segment_sum", dev):
         _lib.check(lib.hn_segment_sum(_ptr(Y), _ptr(rowptr), _ptr(perm), n_rows, C, _ptr(out), _stream(dev)),
                    "hn_segment_sum")
     return out
