@@ -85,7 +85,7 @@ class _EdgeGeometry(Function):
         grad_cell = None
         if want_cell:
             sb = g.seg_batch
-            grad_cell = ops.segment_sum(cellw, sb.rowptr, sb.perm, sb.n_rows).view(-1, 3, 3)
+            grad_cell = ops.segment_sum(cellw, sb.rowptr, sb.perm, sb.n_rows).view(-1, 3, 3)[: g.n_graphs]
         return grad_pos, grad_cell, None
 
 

@@ -65,6 +65,9 @@ class RowGraph:
         self.row_xoff = None          # int64 [R]: row offset of the row's sub-network block in the flat xh buffer
         self.xh_sources, self.xh_base = [], [0]
         self.mod_active = None        # float [M]: 1 if the sub-network has at least one edge (hermnet.py:56-57)
+        self.own_count: List[int] = []  # per type: number of OWNED atoms (they come first inside the type slice);
+        #                                 the rest of the slice are ghost atoms of a domain-decomposed system
+        self.energy_index = None      # int32 [N]: graph id of owned atoms, n_graphs for ghosts
         self._lazy = {}
 
     # ---- lazily built segment views (only the differentiable / training formulation needs them) ----------
@@ -84,9 +87,9 @@ class RowGraph:
         return self._lazy["dst_atom"]
 
     @property
-    def seg_batch(self) -> Segments:    # internal atoms grouped by graph
+    def seg_batch(self) -> Segments:    # internal atoms grouped by graph (ghost atoms fall into the extra last row)
         if "batch" not in self._lazy:
-            self._lazy["batch"] = Segments.from_index(self.atom_graph, self.n_graphs)
+            self._lazy["batch"] = Segments.from_index(self.energy_index, self.n_graphs + 1)
         return self._lazy["batch"]
 
     @property
@@ -115,7 +118,16 @@ class RowGraph:
         return self._lazy[key]
 
     def type_slice(self, t: int) -> slice:
+        """All local atoms (owned, then ghost) of element type ``t``."""
         return slice(self.type_ptr[t], self.type_ptr[t + 1])
+
+    def dst_slice(self, t: int) -> slice:
+        """The owned atoms of type ``t`` -- the rows a sub-network with destination ``t`` updates."""
+        return slice(self.type_ptr[t], self.type_ptr[t] + self.own_count[t])
+
+    @property
+    def n_ghost(self) -> int:
+        return self.n_atoms - sum(self.own_count)
 
 
 class GraphBuilder:
@@ -148,11 +160,21 @@ class GraphBuilder:
         return self._z2t[dev]
 
     # ---------------------------------------------------------------------------------------------------
-    def _order(self, Z: Tensor):
+    def _order(self, Z: Tensor, owned: Optional[Tensor] = None):
+        """Internal order: by element type, owned atoms before ghost atoms inside a type."""
         types = self.z2t(Z.device)[Z.long()]
-        types_sorted, perm = torch.sort(types, stable=True)
-        counts = torch.bincount(types_sorted.long(), minlength=self.T + 1)
-        type_ptr = [0] + torch.cumsum(counts, 0).tolist()          # one host sync per graph build
+        if owned is None:
+            types_sorted, perm = torch.sort(types, stable=True)
+            key_sorted = types_sorted.long() * 2
+        else:
+            key_sorted, perm = torch.sort(types.long() * 2 + (~owned).long(), stable=True)
+            types_sorted = torch.div(key_sorted, 2, rounding_mode="floor")
+        counts = torch.bincount(key_sorted, minlength=2 * (self.T + 1)).view(-1, 2)
+        c = counts.tolist()                                          # one host sync per graph build
+        type_ptr = [0]
+        for t in range(self.T + 1):
+            type_ptr.append(type_ptr[-1] + c[t][0] + c[t][1])
+        self._own_count = [c[t][0] for t in range(self.T + 1)]
         inv = torch.empty_like(perm)
         inv[perm] = torch.arange(perm.numel(), device=perm.device)
         return types_sorted.to(torch.int32).contiguous(), perm, inv, type_ptr
@@ -184,6 +206,28 @@ class GraphBuilder:
         return self.from_coo(n, src=col.long(), dst=centre.long(), shift=-shift, Z=Z, batch=batch,
                              order=(types, perm, inv, type_ptr))
 
+    def from_local_positions(self, pos: Tensor, Z: Tensor, cell: Tensor, owned: Tensor) -> RowGraph:
+        """Domain-decomposed system: ``pos/Z`` are the rank's local atoms (owned + halo candidates) inside the FULL
+        periodic ``cell``; rows are kept for owned destinations only, every local atom may be a source."""
+        dev = pos.device
+        n = pos.size(0)
+        types, perm, inv, type_ptr = self._order(Z, owned)
+        own_count = list(self._own_count)
+        pos32 = pos.detach().to(torch.float32)
+        cell32 = cell.detach().to(torch.float32).reshape(-1, 3, 3).contiguous()
+        gptr = torch.tensor([0, n], dtype=torch.int32, device=dev)
+        G = self.n_groups
+        rowptr, col, shift = ops.radius_graph(pos32[perm].contiguous(), cell32, gptr, self.rc,
+                                              types if G > 1 else None, G, 0)
+        owned_i = owned[perm]
+        lens = (rowptr[1:] - rowptr[:-1]).view(n, G) * owned_i.view(n, 1).to(torch.int32)
+        centre = torch.div(ops.expand_rowptr(rowptr, col.numel()).long(), G, rounding_mode="floor")
+        keep = owned_i[centre]
+        new_rowptr = torch.zeros(n * G + 1, dtype=torch.int32, device=dev)
+        new_rowptr[1:] = torch.cumsum(lens.reshape(-1), 0)
+        return self._finish(n, 1, new_rowptr, col[keep].contiguous(), (-shift[keep]).contiguous(), types, perm, inv,
+                            type_ptr, torch.zeros(n, dtype=torch.int32, device=dev), owned_i, own_count)
+
     def from_edge_index(self, Z: Tensor, edge_index: Tensor, edge_shift: Optional[Tensor], batch: Optional[Tensor]) -> RowGraph:
         """General path for a user-supplied reference-format ``edge_index`` (row 0 = source, row 1 = destination)
         and ``edge_shift``: one stable device sort instead of the reference's per-atom scans."""
@@ -212,16 +256,22 @@ class GraphBuilder:
         return self._finish(n, n_graphs, rowptr, col, shift, types, perm, inv, type_ptr, atom_graph)
 
     # ---------------------------------------------------------------------------------------------------
-    def _finish(self, n, n_graphs, rowptr, col, shift, types, perm, inv, type_ptr, atom_graph) -> RowGraph:
+    def _finish(self, n, n_graphs, rowptr, col, shift, types, perm, inv, type_ptr, atom_graph, owned=None,
+                own_count=None) -> RowGraph:
         """``rowptr/col/shift`` is the base CSR with ``n_groups`` rows per atom (source-element groups)."""
         dev = col.device
         g = RowGraph()
+        g.own_count = list(own_count) if own_count is not None else list(self._own_count)
+        g.energy_index = atom_graph if owned is None else torch.where(
+            owned, atom_graph, torch.full_like(atom_graph, n_graphs)).contiguous()
         g.kind, g.n_atoms, g.n_graphs, g.sign = self.kind, n, n_graphs, self.sign
         g.perm, g.inv_perm, g.types, g.type_ptr, g.atom_graph = perm, inv, types, type_ptr, atom_graph
         g.n_modules = self.n_modules
         T, G = self.T, self.n_groups
         t_long = types.long()
         known = t_long < T
+        if owned is not None:
+            known = known & owned           # ghost atoms are sources only: their rows are inactive
         if self.kind == "HVNet":
             g.rows_per_atom = 1
             g.row_mod = torch.where(known, t_long, torch.full_like(t_long, -1)).to(torch.int32)

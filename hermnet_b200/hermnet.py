@@ -124,8 +124,9 @@ class _HermNet(nn.Module):
             data.x, data.vec = x[g.inv_perm], vec[g.inv_perm]
         return energy
 
-    def forward_graph(self, pos, atomic_number, cell, g: RowGraph):
-        """Hot path on a prebuilt ``RowGraph``: energies ``[num_graphs]`` plus final features (internal order)."""
+    def forward_graph(self, pos, atomic_number, cell, g: RowGraph, halo=None):
+        """Hot path on a prebuilt ``RowGraph``: energies ``[num_graphs]`` plus final features (internal order).
+        ``halo`` (domain decomposition, ``parallel.Halo``) refreshes the ghost rows between layers."""
         F = self.hidden_channels
         fused = self._use_fused(pos)
         pos_i = pos[g.perm]
@@ -139,13 +140,15 @@ class _HermNet(nn.Module):
             p = None
         x = self.embed(z_i)
         vec = torch.zeros((x.size(0), 3, F), dtype=x.dtype, device=x.device)
-        for conv in self.hermconvs:
+        for li, conv in enumerate(self.hermconvs):
+            if halo is not None and li > 0:       # layer 0 reads embeddings / zeros, which every rank has locally
+                x, vec = halo.exchange(x, vec)
             x, vec = self._layer(conv, x, vec, geom, g, p)
         e_atom = self.out_energy(x)                                      # [N,1]   hermnet.py:129
-        energy = Fn.segment_sum(e_atom, g.seg_batch).squeeze(1)          # hermnet.py:130
+        sb = g.seg_batch
+        energy = Fn.segment_sum(e_atom, sb).squeeze(1)[: g.n_graphs]     # hermnet.py:130 (owned atoms only)
         if self.intensive:
-            sb = g.seg_batch
-            energy = energy / (sb.rowptr[1:] - sb.rowptr[:-1]).clamp(min=1).to(energy.dtype)
+            energy = energy / (sb.rowptr[1:] - sb.rowptr[:-1])[: g.n_graphs].clamp(min=1).to(energy.dtype)
         return energy, x, vec
 
     # ------------------------------------------------------------------------------------------------
@@ -171,34 +174,40 @@ class _HermNet(nn.Module):
         dvec = dvec.view(-1, R, 3, F)
         T = len(self.elems)
         xs, vs = [], []
+
+        def pad(n_rows):
+            xs.append(torch.zeros((n_rows, F), dtype=x.dtype, device=x.device))
+            vs.append(torch.zeros((n_rows, 3, F), dtype=x.dtype, device=x.device))
+
         for t in range(T):
-            sl = g.type_slice(t)
-            if sl.stop == sl.start:
-                continue
-            xt, vt = x[sl], vec[sl]
-            x_acc = v_acc = None
-            for m, slots in self._dst_modules(t):
-                mod = mods[m]
-                if self.KIND == "HTNet":
-                    pa = dvec[sl, slots[0]]
-                    pc = dvec[sl, slots[1]] if slots[1] != slots[0] else pa
-                    dxm = dx[sl, slots[0]] + (dx[sl, slots[1]] if slots[1] != slots[0] else 0)
-                    dvm = pa + pc if slots[1] != slots[0] else pa
-                    na = torch.sqrt((pa ** 2).sum(dim=1) + 1e-8)
-                    nc = torch.sqrt((pc ** 2).sum(dim=1) + 1e-8)
-                    vdot = (pa * pc).sum(dim=1) / (na * nc)
-                else:
-                    dxm, dvm, vdot = dx[sl, slots[0]], dvec[sl, slots[0]], None
-                v_new, x_new = mod.node_update(xt, vt, dxm, dvm, vdot)
-                act = g.mod_active[m]                                    # hermnet.py:56-57: no edges -> rows stay 0
-                x_acc = x_new * act if x_acc is None else x_acc + x_new * act
-                v_acc = v_new * act if v_acc is None else v_acc + v_new * act
-            xs.append(x_acc)
-            vs.append(v_acc)
+            sl = g.dst_slice(t)
+            n_ghost_t = g.type_ptr[t + 1] - sl.stop
+            if sl.stop > sl.start:
+                xt, vt = x[sl], vec[sl]
+                x_acc = v_acc = None
+                for m, slots in self._dst_modules(t):
+                    mod = mods[m]
+                    if self.KIND == "HTNet":
+                        pa = dvec[sl, slots[0]]
+                        pc = dvec[sl, slots[1]] if slots[1] != slots[0] else pa
+                        dxm = dx[sl, slots[0]] + (dx[sl, slots[1]] if slots[1] != slots[0] else 0)
+                        dvm = pa + pc if slots[1] != slots[0] else pa
+                        na = torch.sqrt((pa ** 2).sum(dim=1) + 1e-8)
+                        nc = torch.sqrt((pc ** 2).sum(dim=1) + 1e-8)
+                        vdot = (pa * pc).sum(dim=1) / (na * nc)
+                    else:
+                        dxm, dvm, vdot = dx[sl, slots[0]], dvec[sl, slots[0]], None
+                    v_new, x_new = mod.node_update(xt, vt, dxm, dvm, vdot)
+                    act = g.mod_active[m]                                # hermnet.py:56-57: no edges -> rows stay 0
+                    x_acc = x_new * act if x_acc is None else x_acc + x_new * act
+                    v_acc = v_new * act if v_acc is None else v_acc + v_new * act
+                xs.append(x_acc)
+                vs.append(v_acc)
+            if n_ghost_t:
+                pad(n_ghost_t)                                           # ghost rows: refreshed by the halo exchange
         n_unknown = g.type_ptr[T + 1] - g.type_ptr[T]
         if n_unknown:
-            xs.append(torch.zeros((n_unknown, F), dtype=x.dtype, device=x.device))
-            vs.append(torch.zeros((n_unknown, 3, F), dtype=x.dtype, device=x.device))
+            pad(n_unknown)
         return torch.cat(xs, 0), torch.cat(vs, 0)
 
     def _dst_modules(self, t: int):
