@@ -1,0 +1,235 @@
+"""Multi-GPU execution of the hot path: one process per GPU, ``torch.distributed`` (NCCL over NVLink/NVSwitch).
+
+The reference only has data-parallel training (example/dist_train.py:17-143: DDP gradient all-reduce); ``north_star``
+adds spatial domain decomposition for a single large system (BASELINE.json configs[3]).  Both live here.
+
+Domain decomposition (``DomainDecomposition``)
+  * the periodic cell is cut into ``px x py x pz`` fractional bricks, one per rank; positions are replicated (12 MB
+    for 1M atoms), so every rank selects its own atoms plus the halo candidates (within ``rc`` of the brick) locally;
+  * the rank builds a row CSR whose destinations are its OWNED atoms and whose sources are owned + ghost atoms
+    (``GraphBuilder.from_local_positions``); edge shifts keep the full periodicity, a ghost is one row per atom, not
+    per image;
+  * message passing has range ``rc`` per layer, so ghost FEATURES are refreshed before every layer but the first
+    (layer 0 reads embeddings, which are local): ``Halo.exchange`` = pack kernel (``hn_gather_rows``) -> all-to-all
+    -> ghost rows; its backward is the transposed exchange with a deterministic segmented accumulation
+    (``hn_segment_sum``) onto the owners -- the reverse force accumulation;
+  * energies are all-reduced scalars; position gradients of owned and ghost atoms are summed with one all-reduce of
+    the ``[N,3]`` array.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import ops
+from .graph import RowGraph, Segments
+
+Tensor = torch.Tensor
+
+
+def _grid(world: int) -> Tuple[int, int, int]:
+    """Most cubic factorisation px >= py >= pz of ``world``."""
+    best = (world, 1, 1)
+    for a in range(1, world + 1):
+        if world % a:
+            continue
+        for b in range(1, world // a + 1):
+            if (world // a) % b:
+                continue
+            c = world // a // b
+            cand = tuple(sorted((a, b, c), reverse=True))
+            if max(cand) - min(cand) < max(best) - min(best):
+                best = cand
+    return best
+
+
+def _all_to_all(send: Tensor, send_counts: List[int], recv_counts: List[int], group=None) -> Tensor:
+    """Variable-size all-to-all of rows.  NCCL: ``all_to_all_single``; other backends (gloo in the CPU tests):
+    batched point-to-point."""
+    recv = torch.empty((sum(recv_counts),) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
+    if dist.get_backend(group) == "nccl":
+        dist.all_to_all_single(recv, send.contiguous(), recv_counts, send_counts, group=group)
+        return recv
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    so = [0]
+    ro = [0]
+    for c in send_counts:
+        so.append(so[-1] + c)
+    for c in recv_counts:
+        ro.append(ro[-1] + c)
+    recv[ro[rank]:ro[rank + 1]] = send[so[rank]:so[rank + 1]]
+    reqs = []
+    for peer in range(world):
+        if peer == rank:
+            continue
+        if recv_counts[peer]:
+            reqs.append(dist.P2POp(dist.irecv, recv[ro[peer]:ro[peer + 1]], peer, group))
+        if send_counts[peer]:
+            reqs.append(dist.P2POp(dist.isend, send[so[peer]:so[peer + 1]].contiguous(), peer, group))
+    if reqs:
+        for r in dist.batch_isend_irecv(reqs):
+            r.wait()
+    return recv
+
+
+class Halo:
+    """Send / receive lists of one rank.  ``send_idx``: local rows to pack, grouped by destination rank;
+    ``ghost_idx``: local ghost rows in the order the peers send them (grouped by owner rank)."""
+
+    def __init__(self, send_idx: Tensor, send_counts: List[int], ghost_idx: Tensor, recv_counts: List[int],
+                 n_local: int, group=None):
+        self.send_idx = send_idx.to(torch.int32).contiguous()
+        self.ghost_idx = ghost_idx.long().contiguous()
+        self.send_counts, self.recv_counts, self.group, self.n_local = send_counts, recv_counts, group, n_local
+        self.seg_send = Segments.from_index(self.send_idx, n_local)     # adjoint of the pack gather
+        self.bytes_per_exchange = 0
+
+    def exchange(self, x: Tensor, vec: Tensor) -> Tuple[Tensor, Tensor]:
+        F = x.size(1)
+        feat = _HaloExchange.apply(torch.cat([x, vec.reshape(-1, 3 * F)], 1), self)
+        return feat[:, :F], feat[:, F:].reshape(-1, 3, F)
+
+
+class _HaloExchange(Function):
+    @staticmethod
+    def forward(ctx, feat: Tensor, halo: Halo):
+        ctx.halo = halo
+        send = ops.gather_rows(feat.contiguous(), halo.send_idx)
+        recv = _all_to_all(send, halo.send_counts, halo.recv_counts, halo.group)
+        halo.bytes_per_exchange = send.numel() * 4
+        return feat.index_copy(0, halo.ghost_idx, recv)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        halo = ctx.halo
+        g = g.contiguous()
+        back = _all_to_all(g[halo.ghost_idx], halo.recv_counts, halo.send_counts, halo.group)
+        sg = halo.seg_send
+        own = ops.segment_sum(back.contiguous(), sg.rowptr, sg.perm, sg.n_rows)     # reverse accumulation on owners
+        return g.index_fill(0, halo.ghost_idx, 0.0) + own, None
+
+
+class DomainDecomposition:
+    """Energy + forces of ONE periodic system spread over the ranks of ``group`` (inference path)."""
+
+    def __init__(self, model, device, group=None):
+        self.model, self.device, self.group = model, device, group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.grid = _grid(self.world)
+        self.graph: Optional[RowGraph] = None
+        self.halo: Optional[Halo] = None
+
+    # ------------------------------------------------------------------------------------------------------
+    def _assign(self, pos: Tensor, cell: Tensor):
+        """Brick (= owner rank) of every atom and the mask of this rank's local candidates (owned + halo)."""
+        c = cell.reshape(3, 3).double()
+        frac = torch.linalg.solve(c.T, pos.double().T).T
+        frac = frac - torch.floor(frac)
+        vol = torch.det(c).abs()
+        heights = torch.stack([vol / torch.linalg.norm(torch.cross(c[(a + 1) % 3], c[(a + 2) % 3], dim=0)) for a in range(3)])
+        margin = (self.model.rc * (1 + 1e-6) / heights).tolist()
+        owner = torch.zeros(pos.size(0), dtype=torch.long, device=pos.device)
+        local = torch.ones(pos.size(0), dtype=torch.bool, device=pos.device)
+        rk = self.rank
+        coords = []
+        for a in range(3):
+            coords.append(rk % self.grid[a])
+            rk //= self.grid[a]
+        stride = 1
+        for a in range(3):
+            p = self.grid[a]
+            b = torch.clamp((frac[:, a] * p).long(), max=p - 1)
+            owner += b * stride
+            stride *= p
+            if p > 1:
+                lo, hi = coords[a] / p, (coords[a] + 1) / p
+                f = frac[:, a]
+                m = margin[a]
+                inside = torch.zeros_like(local)
+                for k in (-1.0, 0.0, 1.0):            # periodic images of the atom along this axis
+                    inside |= (f + k >= lo - m) & (f + k < hi + m)
+                local &= inside if 2 * m + 1.0 / p < 1.0 else torch.ones_like(local)
+        return owner, local
+
+    def build(self, pos: Tensor, Z: Tensor, cell: Tensor):
+        """Partition + local graph + halo lists for the replicated ``pos [N,3]``, ``Z [N]``, ``cell [1,3,3]``."""
+        dev = pos.device
+        N = pos.size(0)
+        owner, local = self._assign(pos.detach(), cell.detach())
+        ids = torch.nonzero(local).squeeze(1)                          # global ids of local atoms, ascending
+        owned = owner[ids] == self.rank
+        g = self.model.builder.from_local_positions(pos.detach()[ids], Z[ids], cell, owned)
+        gid = ids[g.perm]                                              # global id of each internal local atom
+        n_loc = gid.numel()
+        n_own = sum(g.own_count)
+        owned_i = owned[g.perm]
+        ghost_int = torch.nonzero(~owned_i).squeeze(1)
+        g_owner = owner[gid[ghost_int]]
+        order = torch.argsort(g_owner * N + gid[ghost_int])            # by owner rank, then global id
+        ghost_idx = ghost_int[order]
+        want = gid[ghost_idx]                                          # global ids requested, grouped by owner
+        recv_counts = torch.bincount(g_owner, minlength=self.world).tolist()
+        # tell every owner which of its atoms we need
+        cnt_out = torch.tensor(recv_counts, dtype=torch.long, device=dev)
+        cnt_in = _all_to_all(cnt_out, [1] * self.world, [1] * self.world, self.group)
+        send_counts = cnt_in.tolist()
+        asked = _all_to_all(want, recv_counts, send_counts, self.group)
+        g2l = torch.full((N,), -1, dtype=torch.long, device=dev)
+        g2l[gid] = torch.arange(n_loc, device=dev)
+        send_idx = g2l[asked]
+        self.graph, self.ids = g, ids
+        self.halo = Halo(send_idx, send_counts, ghost_idx, recv_counts, n_loc, self.group)
+        self.Z_local = Z[ids]                                          # local (pre-permutation) order, like pos[ids]
+        self.cell = cell
+        self.n_atoms, self.n_owned = N, n_own
+        stats = torch.tensor([n_own, g.n_edges, n_loc - n_own], dtype=torch.long, device=dev)
+        mx = stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=self.group)
+        sm = stats.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM, group=self.group)
+        self.n_owned_max, self.local_edges_max, self.n_ghost_max = (int(v) for v in mx.tolist())
+        self.global_edges = int(sm[1])
+        assert int(sm[0]) == N, "every atom must be owned by exactly one rank"
+        return self
+
+    def energy_forces(self, pos: Tensor):
+        """Total energy ``[1]`` and ``dE/dpos [N,3]`` (forces = minus that), identical on every rank."""
+        p = pos.detach()[self.ids].requires_grad_(True)
+        e, _, _ = self.model.forward_graph(p, self.Z_local, self.cell, self.graph, halo=self.halo)
+        (gl,) = torch.autograd.grad(e.sum(), p)
+        grad = torch.zeros((self.n_atoms, 3), dtype=gl.dtype, device=gl.device)
+        grad.index_add_(0, self.ids, gl)                               # ids are unique per rank: no collisions
+        e = e.detach().clone()
+        dist.all_reduce(e, group=self.group)
+        dist.all_reduce(grad, group=self.group)
+        return e, grad
+
+
+# ----------------------------------------------------------------------------------------------------------
+# data parallelism (example/dist_train.py:57-67,99)
+# ----------------------------------------------------------------------------------------------------------
+def data_parallel(model, device_ids=None, **kw):
+    """DDP wrapper with ``find_unused_parameters=True``: a rank whose batch lacks an element leaves that
+    sub-network's parameters untouched (hermnet.py:56-57), which plain DDP would wait on forever."""
+    kw.setdefault("find_unused_parameters", True)
+    return torch.nn.parallel.DistributedDataParallel(model, device_ids=device_ids, **kw)
+
+
+def force_matching_step(model, data, optimizer, gamma: float = 0.8, trn_mean: float = 0.0):
+    """One training step of example/dist_train.py:84-104: MSE on energies and on forces obtained with
+    ``create_graph=True`` (double backward through the composite formulation), gradient all-reduce by DDP."""
+    optimizer.zero_grad()
+    data.pos.requires_grad_(True)
+    pred_e = model(data)
+    e_loss = torch.nn.functional.mse_loss(pred_e, data.y - trn_mean)
+    pred_f = -torch.autograd.grad(pred_e.sum(), data.pos, create_graph=True)[0]
+    f_loss = torch.nn.functional.mse_loss(pred_f, data.forces)
+    loss = (1 - gamma) * e_loss + gamma * f_loss
+    loss.backward()
+    optimizer.step()
+    return loss.detach(), pred_e.detach(), pred_f.detach()

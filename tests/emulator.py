@@ -245,3 +245,12 @@ def install(monkeypatch):
     monkeypatch.setattr(ops, "require_cuda", lambda t, what: None)
     monkeypatch.setattr(ops, "compute_device", lambda t: t.device)
     monkeypatch.setattr(ops, "sm_count", lambda: 148)
+
+
+def install_plain():
+    """Same as ``install`` for spawned worker processes (no pytest monkeypatch there)."""
+    class _MP:
+        @staticmethod
+        def setattr(obj, name, value):
+            setattr(obj, name, value)
+    install(_MP)
