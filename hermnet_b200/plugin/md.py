@@ -1,0 +1,103 @@
+"""ASE-free MD driver for BASELINE.json configs[2] ("MD inference via the ASE calculator plugin"): ASE is not
+installed in this image, so this module supplies the two pieces of ASE the plugin path needs -- an ``Atoms``-like
+container and a velocity-Verlet loop -- with ASE's attribute names, so ``NNCalculator`` is exercised exactly as ASE
+would drive it (``atoms.get_forces()`` -> ``calc.calculate(atoms)``).  ``device_resident=True`` is SURVEY 8(f) rank 1:
+positions stay on the GPU and only the graph is rebuilt per step."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from ..data import Data
+from ..symbols import atomic_numbers, chemical_symbols
+
+KB_EV = 8.617333262e-5
+AMU_A2_FS2_TO_EV = 103.642697      # 1 amu*A^2/fs^2 in eV
+MASSES = {1: 1.008, 3: 6.94, 6: 12.011, 8: 15.999, 13: 26.982, 14: 28.085, 24: 51.996, 25: 54.938, 26: 55.845,
+          27: 58.933, 28: 58.693}
+
+
+class SimpleAtoms:
+    """The subset of ``ase.Atoms`` the calculator touches."""
+
+    def __init__(self, numbers, positions, cell=None, pbc=True):
+        self.numbers = np.asarray(numbers)
+        self.positions = np.asarray(positions, dtype=np.float64)
+        self.cell = None if cell is None else np.asarray(cell, dtype=np.float64).reshape(3, 3)
+        self.pbc = np.array([bool(pbc)] * 3)
+        self.calc = None
+        self.velocities = np.zeros_like(self.positions)
+
+    def get_chemical_symbols(self):
+        return [chemical_symbols[z] for z in self.numbers]
+
+    def todict(self):
+        return {"cell": self.cell, "positions": self.positions, "numbers": self.numbers, "pbc": self.pbc}
+
+    def get_masses(self):
+        return np.array([MASSES.get(int(z), 2.0 * int(z)) for z in self.numbers])
+
+    def get_forces(self):
+        self.calc.calculate(self, ["forces"])
+        return self.calc.results["forces"]
+
+    def get_potential_energy(self):
+        self.calc.calculate(self, ["energy"])
+        return self.calc.results["energy"]
+
+    def __len__(self):
+        return len(self.numbers)
+
+
+def maxwell_boltzmann(atoms: SimpleAtoms, temperature_K: float, seed: int = 0):
+    rng = np.random.default_rng(seed)
+    m = atoms.get_masses()[:, None] * AMU_A2_FS2_TO_EV
+    atoms.velocities = rng.normal(size=atoms.positions.shape) * np.sqrt(KB_EV * temperature_K / m)
+    atoms.velocities -= atoms.velocities.mean(0, keepdims=True)
+
+
+def velocity_verlet(atoms: SimpleAtoms, steps: int, dt_fs: float = 0.5):
+    """Host-driven loop, one ``calculate`` per step (what ASE's ``VelocityVerlet`` does)."""
+    m = atoms.get_masses()[:, None] * AMU_A2_FS2_TO_EV
+    f = atoms.get_forces()
+    energies = []
+    for _ in range(steps):
+        atoms.velocities += 0.5 * dt_fs * f / m
+        atoms.positions = atoms.positions + dt_fs * atoms.velocities
+        f = atoms.get_forces()
+        atoms.velocities += 0.5 * dt_fs * f / m
+        energies.append(atoms.calc.results["energy"])
+    return energies
+
+
+@torch.no_grad()
+def _kick(v, f, inv_m, dt):
+    v.add_(f * inv_m, alpha=0.5 * dt)
+
+
+def velocity_verlet_device(model, numbers, positions, cell, velocities, steps: int, dt_fs: float = 0.5, device="cuda"):
+    """Device-resident MD: positions, velocities and forces never leave the GPU; per step only the
+    neighbour list / row CSR is rebuilt (device cell list) and one scalar energy may be read back by the caller."""
+    dev = torch.device(device)
+    Z = torch.as_tensor(np.asarray(numbers)).long().to(dev)
+    pos = torch.as_tensor(np.asarray(positions), dtype=torch.float32).to(dev)
+    vel = torch.as_tensor(np.asarray(velocities), dtype=torch.float32).to(dev)
+    c = torch.as_tensor(np.asarray(cell), dtype=torch.float32).reshape(1, 3, 3).to(dev)
+    masses = np.array([MASSES.get(int(z), 2.0 * int(z)) for z in np.asarray(numbers)])
+    inv_m = torch.as_tensor(1.0 / (masses * AMU_A2_FS2_TO_EV), dtype=torch.float32).to(dev)[:, None]
+
+    def forces(p):
+        d = Data(pos=p.detach().requires_grad_(True), atomic_number=Z, cell=c)
+        e = model(d)
+        (g,) = torch.autograd.grad(e.sum(), d.pos)
+        return e.detach(), -g
+
+    e, f = forces(pos)
+    energies = []
+    for _ in range(steps):
+        _kick(vel, f, inv_m, dt_fs)
+        pos = pos + dt_fs * vel
+        e, f = forces(pos)
+        _kick(vel, f, inv_m, dt_fs)
+        energies.append(e)
+    return pos, vel, torch.cat(energies)
