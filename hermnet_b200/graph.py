@@ -196,7 +196,7 @@ class GraphBuilder:
                                                   types if self.n_groups > 1 else None, self.n_groups, 0)
             shift = -shift    # centre-row entry (j, S') is the reference edge (src=j, dst=centre, S=-S')
             return self._finish(n, n_graphs, rowptr, col, shift, types, perm, inv, type_ptr,
-                                torch.zeros(n, dtype=torch.int32, device=dev))
+                                torch.zeros(n, dtype=torch.int32, device=dev), pos_i=pos32[perm].contiguous(), cell=cell32)
         # batches / capped lists: search in the original (graph-contiguous) order, then regroup
         b = torch.zeros(n, dtype=torch.long, device=dev) if batch is None else batch.long()
         gptr = torch.zeros(n_graphs + 1, dtype=torch.int32, device=dev)
@@ -204,7 +204,7 @@ class GraphBuilder:
         rowptr, col, shift = ops.radius_graph(pos32.contiguous(), cell32, gptr, self.rc, None, 1, max_neighbors)
         centre = ops.expand_rowptr(rowptr, col.numel())
         return self.from_coo(n, src=col.long(), dst=centre.long(), shift=-shift, Z=Z, batch=batch,
-                             order=(types, perm, inv, type_ptr))
+                             order=(types, perm, inv, type_ptr), pos=pos32, cell=cell32)
 
     def from_local_positions(self, pos: Tensor, Z: Tensor, cell: Tensor, owned: Tensor) -> RowGraph:
         """Domain-decomposed system: ``pos/Z`` are the rank's local atoms (owned + halo candidates) inside the FULL
@@ -226,19 +226,23 @@ class GraphBuilder:
         new_rowptr = torch.zeros(n * G + 1, dtype=torch.int32, device=dev)
         new_rowptr[1:] = torch.cumsum(lens.reshape(-1), 0)
         return self._finish(n, 1, new_rowptr, col[keep].contiguous(), (-shift[keep]).contiguous(), types, perm, inv,
-                            type_ptr, torch.zeros(n, dtype=torch.int32, device=dev), owned_i, own_count)
+                            type_ptr, torch.zeros(n, dtype=torch.int32, device=dev), owned_i, own_count,
+                            pos_i=pos32[perm].contiguous(), cell=cell32)
 
-    def from_edge_index(self, Z: Tensor, edge_index: Tensor, edge_shift: Optional[Tensor], batch: Optional[Tensor]) -> RowGraph:
+    def from_edge_index(self, Z: Tensor, edge_index: Tensor, edge_shift: Optional[Tensor], batch: Optional[Tensor],
+                        pos: Optional[Tensor] = None, cell: Optional[Tensor] = None) -> RowGraph:
         """General path for a user-supplied reference-format ``edge_index`` (row 0 = source, row 1 = destination)
         and ``edge_shift``: one stable device sort instead of the reference's per-atom scans."""
         shift = None
         if edge_shift is not None:
             s = torch.round(edge_shift).to(torch.int8)
             shift = torch.cat([s, torch.zeros((s.size(0), 1), dtype=torch.int8, device=s.device)], 1)
-        return self.from_coo(Z.numel(), edge_index[0].long(), edge_index[1].long(), shift, Z, batch)
+        pos32 = None if pos is None else pos.detach().to(torch.float32)
+        cell32 = None if (cell is None or edge_shift is None) else cell.detach().to(torch.float32).reshape(-1, 3, 3).contiguous()
+        return self.from_coo(Z.numel(), edge_index[0].long(), edge_index[1].long(), shift, Z, batch, pos=pos32, cell=cell32)
 
     def from_coo(self, n: int, src: Tensor, dst: Tensor, shift: Optional[Tensor], Z: Tensor, batch: Optional[Tensor],
-                 order=None) -> RowGraph:
+                 order=None, pos: Optional[Tensor] = None, cell: Optional[Tensor] = None) -> RowGraph:
         dev = Z.device
         types, perm, inv, type_ptr = order if order is not None else self._order(Z)
         n_graphs = 1 if batch is None else (int(batch.max().item()) + 1 if n else 1)
@@ -253,13 +257,32 @@ class GraphBuilder:
             shift = shift[order_e.long()].contiguous()
         atom_graph = (torch.zeros(n, dtype=torch.int32, device=dev) if batch is None
                       else batch[perm].to(torch.int32).contiguous())
-        return self._finish(n, n_graphs, rowptr, col, shift, types, perm, inv, type_ptr, atom_graph)
+        return self._finish(n, n_graphs, rowptr, col, shift, types, perm, inv, type_ptr, atom_graph,
+                            pos_i=None if pos is None else pos[perm].contiguous(), cell=cell)
 
     # ---------------------------------------------------------------------------------------------------
+    def _distance_bins(self, pos_i, cell, atom_graph, rowptr, col, shift, rows_per_atom) -> Tensor:
+        """8-bit distance bin of every entry of a CSR (positions in internal order) -- the sort key that makes the
+        Gaussian bands of consecutive row entries overlap (csrc/hn_edge.cu)."""
+        from types import SimpleNamespace
+        e = int(col.numel())
+        tmp = SimpleNamespace(atom_graph=atom_graph, edge_row=ops.expand_rowptr(rowptr, e), rows_per_atom=rows_per_atom,
+                              col=col, shift=shift, sign=self.sign, n_edges=e)
+        d = ops.edge_geom_fwd(pos_i, cell, tmp)[:, 3]
+        return torch.clamp(d * (255.0 / self.rc), max=255.0).to(torch.int32).contiguous(), tmp.edge_row
+
     def _finish(self, n, n_graphs, rowptr, col, shift, types, perm, inv, type_ptr, atom_graph, owned=None,
-                own_count=None) -> RowGraph:
+                own_count=None, pos_i=None, cell=None) -> RowGraph:
         """``rowptr/col/shift`` is the base CSR with ``n_groups`` rows per atom (source-element groups)."""
         dev = col.device
+        dbin = None
+        if pos_i is not None and col.numel() > 0:
+            # sort every base row by distance (stable two-pass: distance bin, then row)
+            dbin, base_row = self._distance_bins(pos_i, cell, atom_graph, rowptr, col, shift, self.n_groups)
+            o1 = ops.sort_by_key(dbin, 256)[1].long()
+            o2 = ops.sort_by_key(base_row[o1].contiguous(), n * self.n_groups)[1].long()
+            order = o1[o2]
+            col, shift, dbin = col[order].contiguous(), shift[order].contiguous(), dbin[order].contiguous()
         g = RowGraph()
         g.own_count = list(own_count) if own_count is not None else list(self._own_count)
         g.energy_index = atom_graph if owned is None else torch.where(
@@ -297,6 +320,8 @@ class GraphBuilder:
             base_row = atom_of * G + sel[slot]
             base_e = rowptr.long()[base_row] + (torch.arange(e_new, device=dev) - new_rowptr.long()[new_edge_row])
             col, shift, rowptr = col[base_e].contiguous(), shift[base_e].contiguous(), new_rowptr
+            if dbin is not None:
+                dbin = dbin[base_e].contiguous()
             pidx = torch.arange(P, device=dev).repeat_interleave(2).view(1, -1).expand(n, 2 * P)
             mod = t_long.view(n, 1) * P + pidx
             ok = known.view(n, 1) & (live.view(1, -1) > 0)
@@ -328,7 +353,17 @@ class GraphBuilder:
         g.n_edges = int(col.numel())
         g.row_mod = g.row_mod.contiguous()
         g.edge_row = ops.expand_rowptr(g.rowptr, g.n_edges)
-        g.t_rowptr, g.t_eid = ops.sort_by_key(g.col, n)
+        # transposed view, every source row sorted by (module, distance) so that tiles of consecutive entries share
+        # the module's filter rows (edge_bwd_src_kernel)
+        M1 = self.n_modules + 1
+        major = (g.col.long() * M1 + (g.row_mod[g.edge_row.long()].long() + 1)).to(torch.int32).contiguous()
+        if dbin is not None and g.n_edges > 0:
+            o1 = ops.sort_by_key(dbin, 256)[1].long()
+            rp, o2 = ops.sort_by_key(major[o1].contiguous(), n * M1)
+            g.t_eid = o1[o2.long()].to(torch.int32).contiguous()
+        else:
+            rp, g.t_eid = ops.sort_by_key(major, n * M1)
+        g.t_rowptr = rp[::M1].contiguous()
         lens = (g.rowptr[1:] - g.rowptr[:-1]).long()
         cnt = torch.zeros(self.n_modules + 1, dtype=torch.long, device=dev)
         cnt.index_add_(0, torch.where(g.row_mod >= 0, g.row_mod.long(), torch.full_like(lens, self.n_modules)), lens)

@@ -95,7 +95,8 @@ class _HermNet(nn.Module):
         batch = data.get("batch")
         ei = data.get("edge_index")
         if ei is not None:
-            g = self.builder.from_edge_index(data.atomic_number, ei, data.get("edge_shift"), batch)
+            g = self.builder.from_edge_index(data.atomic_number, ei, data.get("edge_shift"), batch,
+                                             pos=data.pos, cell=data.get("cell"))
         else:
             g = self.builder.from_positions(data.pos, data.atomic_number, data.get("cell"), batch)
         data.graph = g

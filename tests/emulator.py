@@ -4,7 +4,7 @@ The product has no CPU path.  To exercise the HOST logic (graph building, row la
 classes, DDP / halo plumbing under gloo) without a GPU, ``install(monkeypatch)`` swaps every function of
 ``hermnet_b200.ops`` for a torch-CPU function with the same contract.  The emulated edge / geometry backward
 functions follow the formulas of the CUDA kernels (csrc/hn_edge.cu, hn_geom.cu) line by line -- including the
-16-wide Gaussian band -- so that the maths of the hand-written backward is checked against autograd of the
+12-wide Gaussian band -- so that the maths of the hand-written backward is checked against autograd of the
 oracle on the CPU; the kernels themselves are checked on the GPU by the ``-m gpu`` tests.
 """
 from __future__ import annotations
@@ -128,12 +128,12 @@ def edge_num_slices(hidden):
 
 
 def _band(p, geom, offset, deriv=False):
-    """val[e, k] (and dval) with the kernel's 16-wide band; zeros outside the band / beyond the cutoff."""
+    """val[e, k] (and dval) with the kernel's 12-wide band; zeros outside the band / beyond the cutoff."""
     K = p.num_rbf
     u = geom[:, 3] * p.inv_rc
-    nb = min(16, K)
+    nb = min(12, K)
     kc = torch.floor(u * (K - 1)).long()
-    k0 = (kc - 7).clamp(min=0).clamp(max=K - nb)
+    k0 = (kc - 5).clamp(min=0).clamp(max=K - nb)
     k = torch.arange(K)[None, :]
     inband = (k >= k0[:, None]) & (k < k0[:, None] + nb) & (u < 1)[:, None]
     pp = p.env_p

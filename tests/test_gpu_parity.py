@@ -234,8 +234,9 @@ def test_mid_size_fused_equals_composite_and_invariances(kind, F):
     model.edge_path = "fused"
     d = H.Data(pos=(p + torch.tensor([0.37, -1.1, 2.9], device=DEV)).requires_grad_(True), atomic_number=z, cell=c)
     e2, f2, _ = util.energy_forces(model, d)
-    assert util.rel_err(e2, out["fused"][0]) < 2e-5
-    assert float((f2 - out["fused"][1]).abs().max()) < 2e-4 * fscale
+    # a rigid shift re-rounds every fp32 coordinate (~1e-6 A); random weights give force constants ~1e3 eV/A^2
+    assert util.rel_err(e2, out["fused"][0]) < 5e-5
+    assert float((f2 - out["fused"][1]).abs().max()) < 1e-3 * fscale
 
 
 def test_c2_graph_vs_oracle_4096_atoms():
@@ -251,3 +252,39 @@ def test_c2_graph_vs_oracle_4096_atoms():
                                  torch.from_numpy(cell)[None], es)
     assert util.rel_err(e.cpu(), eo) < TOL_E
     assert float((f.cpu() - fo).abs().max()) < TOL_F
+
+
+def test_ase_style_calculator_md_and_batched_displacements():
+    """BASELINE configs[2] path: NNCalculator driven like ASE drives it, device-resident MD, batched force sets."""
+    import sys, os
+    from hermnet_b200.plugin import NNCalculator
+    from hermnet_b200.plugin import md
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from plugin.phonopy_interface.phonon_calc import batched_force_sets
+    pos, Z, cell = synthetic.water_box(3, seed=3)
+    cfg = dict(elems=["H", "O"], rc=4.0, num_layers=2, hidden_channels=64, num_rbf=32)
+    model, sd = util.make_model("HTNet", cfg, 31, DEV, pbc_shift="physical")
+    calc = NNCalculator(model, None, trn_mean=-1.5, device_=DEV, ensemble="NPT")
+    atoms = md.SimpleAtoms(Z, pos, cell)
+    atoms.calc = calc
+    f = atoms.get_forces()
+    assert set(calc.results) == {"energy", "free_energy", "forces", "stress"} and calc.results["stress"].shape == (6,)
+    ei, es = H.neighbor_search(torch.from_numpy(pos), 4.0, torch.from_numpy(cell)[None])
+    eo, fo = O.energy_and_forces("HTNet", sd, cfg, torch.from_numpy(pos), torch.from_numpy(Z), ei,
+                                 torch.from_numpy(cell)[None], es, pbc_shift="physical")
+    assert abs(calc.results["energy"] - (float(eo) - 1.5)) < 1e-4 * abs(float(eo)) + 1e-4
+    assert float(np.abs(f - fo.numpy()).max()) < TOL_F * max(1.0, float(fo.abs().max()))
+    # host-driven and device-resident velocity Verlet follow the same trajectory
+    md.maxwell_boltzmann(atoms, 300.0, seed=3)
+    v0 = atoms.velocities.copy()
+    e_host = md.velocity_verlet(atoms, steps=5, dt_fs=0.5)
+    p_dev, v_dev, e_dev = md.velocity_verlet_device(model, Z, pos, cell, v0, steps=5, dt_fs=0.5, device=DEV)
+    assert float(np.abs(p_dev.cpu().numpy() - atoms.positions).max()) < 1e-3
+    assert abs(float(e_dev[-1]) - (e_host[-1] + 1.5)) < 1e-3 * max(1.0, abs(e_host[-1]))
+    # all displaced cells in one batched forward == one at a time
+    rng = np.random.default_rng(0)
+    disp = [pos + rng.normal(0, 0.01, pos.shape).astype(np.float32) for _ in range(5)]
+    fb = batched_force_sets(model, Z, cell, disp, device=DEV)
+    for k, p in enumerate(disp):
+        atoms.positions = p.astype(np.float64)
+        assert float(np.abs(fb[k] - atoms.get_forces()).max()) < TOL_F * max(1.0, float(np.abs(fb[k]).max()))
