@@ -64,6 +64,7 @@ class RowGraph:
         self.type_ptr: List[int] = []  # host offsets of the type slices, len T+2 (last slice = unknown elements)
         self.row_xoff = None          # int64 [R]: row offset of the row's sub-network block in the flat xh buffer
         self.xh_sources, self.xh_base = [], [0]
+        self.mod_active_host: List[bool] = []
         self.mod_active = None        # float [M]: 1 if the sub-network has at least one edge (hermnet.py:56-57)
         self.own_count: List[int] = []  # per type: number of OWNED atoms (they come first inside the type slice);
         #                                 the rest of the slice are ghost atoms of a domain-decomposed system
@@ -368,4 +369,5 @@ class GraphBuilder:
         cnt = torch.zeros(self.n_modules + 1, dtype=torch.long, device=dev)
         cnt.index_add_(0, torch.where(g.row_mod >= 0, g.row_mod.long(), torch.full_like(lens, self.n_modules)), lens)
         g.mod_active = (cnt[: self.n_modules] > 0).to(torch.float32)
+        g.mod_active_host = (cnt[: self.n_modules] > 0).tolist()   # (graph build already synchronises)
         return g

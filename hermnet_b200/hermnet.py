@@ -157,10 +157,26 @@ class _HermNet(nn.Module):
         F = self.hidden_channels
         mods = list(conv.mods.values())
         # node side, part 1: projected source features of every sub-network, compact (graph.xh_sources)
+        # LayerNorm_m(x) = xhat * gamma_m + beta_m shares the normalisation: xhat is computed ONCE per layer and the
+        # affine part is folded into the first Linear of every sub-network (W1.diag(gamma), b1 + W1.beta) -- the
+        # reference runs a full LayerNorm pass over all N rows per sub-network (rmnet.py:52).
+        xhat = torch.nn.functional.layer_norm(x, (F,), None, None, mods[0].message_layer.x_layernorm.eps)
+        w1s, b1s = [], []
+        for mod in mods:
+            ml = mod.message_layer
+            w1s.append(ml.x_proj[0].weight * ml.x_layernorm.weight[None, :])
+            b1s.append(ml.x_proj[0].bias + ml.x_proj[0].weight @ ml.x_layernorm.bias)
         blocks = []
-        for mod, srcs in zip(mods, g.xh_sources):
-            rows = x[srcs[0][0]:srcs[0][1]] if len(srcs) == 1 else torch.cat([x[lo:hi] for lo, hi in srcs], 0)
-            blocks.append(mod.message_layer.node_features(rows))
+        if self.KIND == "HVNet":     # every sub-network reads every row: one [N,F]x[F,M*F] GEMM for the first Linear
+            h = mods[0].message_layer.x_proj[1](torch.addmm(torch.cat(b1s), xhat, torch.cat(w1s, 0).t()))
+            for m, mod in enumerate(mods):
+                l2 = mod.message_layer.x_proj[2]
+                blocks.append(torch.nn.functional.linear(h[:, m * F:(m + 1) * F], l2.weight, l2.bias))
+        else:
+            for mod, srcs, w1, b1 in zip(mods, g.xh_sources, w1s, b1s):
+                rows = xhat[srcs[0][0]:srcs[0][1]] if len(srcs) == 1 else torch.cat([xhat[lo:hi] for lo, hi in srcs], 0)
+                ml = mod.message_layer
+                blocks.append(ml.x_proj[2](ml.x_proj[1](torch.addmm(b1, rows, w1.t()))))
         xh = torch.cat(blocks, 0)                                        # [rows, 3F]
         Wt = torch.stack([m.message_layer.rbf_proj.weight.t() for m in mods])   # [M,K,3F]
         bias = torch.stack([m.message_layer.rbf_proj.bias for m in mods])       # [M,3F]
@@ -198,12 +214,16 @@ class _HermNet(nn.Module):
                         vdot = (pa * pc).sum(dim=1) / (na * nc)
                     else:
                         dxm, dvm, vdot = dx[sl, slots[0]], dvec[sl, slots[0]], None
+                    if not g.mod_active_host[m]:                         # hermnet.py:56-57: no edges -> rows stay 0
+                        continue
                     v_new, x_new = mod.node_update(xt, vt, dxm, dvm, vdot)
-                    act = g.mod_active[m]                                # hermnet.py:56-57: no edges -> rows stay 0
-                    x_acc = x_new * act if x_acc is None else x_acc + x_new * act
-                    v_acc = v_new * act if v_acc is None else v_acc + v_new * act
-                xs.append(x_acc)
-                vs.append(v_acc)
+                    x_acc = x_new if x_acc is None else x_acc + x_new
+                    v_acc = v_new if v_acc is None else v_acc + v_new
+                if x_acc is None:
+                    pad(sl.stop - sl.start)
+                else:
+                    xs.append(x_acc)
+                    vs.append(v_acc)
             if n_ghost_t:
                 pad(n_ghost_t)                                           # ghost rows: refreshed by the halo exchange
         n_unknown = g.type_ptr[T + 1] - g.type_ptr[T]

@@ -164,6 +164,9 @@ class DomainDecomposition:
         ids = torch.nonzero(local).squeeze(1)                          # global ids of local atoms, ascending
         owned = owner[ids] == self.rank
         g = self.model.builder.from_local_positions(pos.detach()[ids], Z[ids], cell, owned)
+        act = g.mod_active.clone()            # "sub-network has no edges" (hermnet.py:56-57) is a GLOBAL property
+        dist.all_reduce(act, op=dist.ReduceOp.MAX, group=self.group)
+        g.mod_active, g.mod_active_host = act, (act > 0).tolist()
         gid = ids[g.perm]                                              # global id of each internal local atom
         n_loc = gid.numel()
         n_own = sum(g.own_count)
