@@ -1,0 +1,284 @@
+// Split-precision dense GEMM on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a only.
+//
+//   C[M,N] = A[M,K] . W[N,K]^T (+ bias[N])          fp32 in, fp32 out, fp32-class accuracy
+//
+// Replaces the cuBLAS fp32 SIMT GEMMs behind the node-side nn.Linear layers of the reference
+// (HermNet/rmnet.py:40-49,84-89: x_proj, vec_proj, xvec_proj; hermnet.py:112-116 out_energy) on the fused
+// (inference) path.  fp32 parity (BASELINE: 1e-5 relative energies) rules out single-pass TF32, so every operand
+// is split  a = hi + lo  with  hi = a & 0xFFFFE000 (exactly representable in TF32)  and  lo = a - hi  (exact in
+// fp32, <= 13 significant bits), and the product is accumulated in TMEM as
+//     hi.hi + hi.lo + lo.hi                      (3 x tcgen05.mma.kind::tf32, fp32 accumulate)
+// the dropped lo.lo term is <= 2^-22 relative.  W is split once on the host side; A is split in shared memory by the
+// CTA that consumes it (an elementwise op, so it is oblivious to the 128-byte swizzle TMA wrote).
+//
+// CTA = one 128 x BN output tile, 256 threads:
+//   warp 0   : TMA producer (A raw, W_hi, W_lo K-chunks of 32 floats = one 128-byte swizzle row), 3-stage ring
+//   warp 1   : MMA issuer (one thread), tcgen05.commit releases the stage / signals the epilogue
+//   warp 2   : TMEM allocation
+//   warps 4-7: split A in place (hi) + side buffer (lo), then epilogue: tcgen05.ld 32x32b -> +bias -> st.global
+#include <cuda.h>
+
+#include "hn_common.cuh"
+
+namespace {
+
+constexpr int BM = 128, BK = 32, STAGES = 3;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra.uni WAIT_DONE;\n\t"
+        "bra.uni WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}\n" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+// K-major, 128-byte swizzle, rows of 128 B, 8-row groups 1024 B apart (SBO = 64), LBO = 1, descriptor version 1
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+template <int BN>
+struct Smem {
+    static constexpr int kA = BM * BK * 4;   // 16 KB
+    static constexpr int kB = BN * BK * 4;
+    static constexpr int kStage = 2 * kA + 2 * kB;
+    static constexpr int kBars = STAGES * kStage;
+    static constexpr int kTotal = kBars + 256 + 1024;   // barriers + tmem slot, + slack for 1024-byte alignment
+};
+
+template <int BN>
+__global__ void __launch_bounds__(256, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
+                   const __grid_constant__ CUtensorMap tmBlo, const float *__restrict__ bias, float *__restrict__ C,
+                   int M, int N, int K, long long ldc) {
+    extern __shared__ uint8_t smem_raw[];
+    using L = Smem<BN>;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bars = base + L::kBars;
+    const uint32_t full0 = bars, split0 = bars + 8 * STAGES, empty0 = bars + 16 * STAGES, tfull = bars + 24 * STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gen + L::kBars + 24 * STAGES + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+    const int num_k = K / BK;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(split0 + 8 * s, 128);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        mbar_init(tfull, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        constexpr uint32_t cols = BN < 32 ? 32 : BN;   // power of two >= 32
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(cols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < num_k; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (kb / STAGES) & 1;
+                mbar_wait(empty0 + 8 * s, ph ^ 1);
+                const uint32_t st = base + s * L::kStage;
+                mbar_expect_tx(full0 + 8 * s, L::kA + 2 * L::kB);
+                tma_load_2d(st, &tmA, full0 + 8 * s, kb * BK, m0);
+                tma_load_2d(st + 2 * L::kA, &tmBhi, full0 + 8 * s, kb * BK, n0);
+                tma_load_2d(st + 2 * L::kA + L::kB, &tmBlo, full0 + 8 * s, kb * BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        // instruction descriptor: D=F32 (bit 4), A=B=TF32 (2<<7, 2<<10), K-major A and B, N>>3 at bit 17, M>>4 at bit 24
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        for (int kb = 0; kb < num_k; ++kb) {
+            const int s = kb % STAGES;
+            const uint32_t ph = (kb / STAGES) & 1;
+            mbar_wait(full0 + 8 * s, ph);
+            mbar_wait(split0 + 8 * s, ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                const uint32_t st = base + s * L::kStage;
+                const uint32_t a_hi = st, a_lo = st + L::kA, b_hi = st + 2 * L::kA, b_lo = b_hi + L::kB;
+#pragma unroll
+                for (int k4 = 0; k4 < BK / 8; ++k4) {
+                    const uint32_t off = k4 * 32;   // 8 tf32 = 32 bytes inside the 128-byte swizzle row
+                    umma_tf32(tmem_base, umma_desc(a_hi + off), umma_desc(b_hi + off), idesc, (kb | k4) != 0);
+                    umma_tf32(tmem_base, umma_desc(a_hi + off), umma_desc(b_lo + off), idesc, 1);
+                    umma_tf32(tmem_base, umma_desc(a_lo + off), umma_desc(b_hi + off), idesc, 1);
+                }
+                umma_commit(empty0 + 8 * s);                 // stage free once these MMAs retire
+                if (kb == num_k - 1) umma_commit(tfull);     // accumulator complete
+            }
+            __syncwarp();
+        }
+    } else if (warp >= 4) {
+        const int t = threadIdx.x - 128;
+        for (int kb = 0; kb < num_k; ++kb) {
+            const int s = kb % STAGES;
+            const uint32_t ph = (kb / STAGES) & 1;
+            mbar_wait(full0 + 8 * s, ph);
+            float4 *hi = reinterpret_cast<float4 *>(gen + s * L::kStage);
+            float4 *lo = reinterpret_cast<float4 *>(gen + s * L::kStage + L::kA);
+#pragma unroll
+            for (int i = 0; i < L::kA / 16 / 128; ++i) {
+                const float4 v = hi[t + i * 128];
+                float4 h, l;
+                h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+                h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+                h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+                h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+                hi[t + i * 128] = h;
+                lo[t + i * 128] = l;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
+            mbar_arrive(split0 + 8 * s);
+        }
+        // epilogue: warp w of this group owns TMEM lanes 32*(w%4) .. +31 = output rows m0 + 32*(w%4) + lane
+        mbar_wait(tfull, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp & 3;
+        const long long row = (long long)m0 + q * 32 + lane;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                  "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                  "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (row < M) {
+                float *dst = C + row * ldc + n0 + c0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 o = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                           __uint_as_float(r[j + 3]));
+                    if (bias != nullptr) {
+                        const float4 b = __ldg(reinterpret_cast<const float4 *>(bias + n0 + c0 + j));
+                        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                    }
+                    *reinterpret_cast<float4 *>(dst + j) = o;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        constexpr uint32_t cols = BN < 32 ? 32 : BN;
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(cols));
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// [rows, K] fp32 row-major with row pitch ld (floats): box = 32 floats (128 B, one swizzle row) x box_rows
+int make_map(CUtensorMap *map, const float *ptr, int64_t rows, int64_t K, int64_t ld, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (enc == nullptr) return 1;
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+    cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : 2;
+}
+
+template <int BN>
+int launch(const float *A, int64_t M, int64_t K, int64_t lda, const float *Whi, const float *Wlo, int64_t N, const float *bias,
+           float *C, int64_t ldc, cudaStream_t st) {
+    const char *where = "hn_gemm_tf32x3";
+    CUtensorMap ta, tbh, tbl;
+    HN_REQUIRE(make_map(&ta, A, M, K, lda, BM) == 0, where, "cuTensorMapEncodeTiled failed for A");
+    HN_REQUIRE(make_map(&tbh, Whi, N, K, K, BN) == 0, where, "cuTensorMapEncodeTiled failed for W_hi");
+    HN_REQUIRE(make_map(&tbl, Wlo, N, K, K, BN) == 0, where, "cuTensorMapEncodeTiled failed for W_lo");
+    static bool attr_set = false;
+    if (!attr_set) {
+        HN_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::kTotal), where);
+        attr_set = true;
+    }
+    dim3 grid((unsigned)(N / BN), (unsigned)((M + BM - 1) / BM));
+    gemm_tf32x3_kernel<BN><<<grid, 256, Smem<BN>::kTotal, st>>>(ta, tbh, tbl, bias, C, (int)M, (int)N, (int)K, (long long)ldc);
+    return hn::check_launch(where);
+}
+
+}  // namespace
+
+// C[M,N] (row pitch ldc) = A[M,K] (row pitch lda) . W[N,K]^T + bias;  W given pre-split (hi = W & 0xFFFFE000, lo = W - hi).
+// Requirements: K % 32 == 0, N % 64 == 0, lda % 4 == 0, 16-byte aligned pointers.
+extern "C" int hn_gemm_tf32x3(const float *A, int64_t M, int64_t K, int64_t lda, const float *W_hi, const float *W_lo, int64_t N,
+                              const float *bias, float *C, int64_t ldc, void *stream) {
+    const char *where = "hn_gemm_tf32x3";
+    if (M <= 0) return 0;
+    HN_REQUIRE(K >= 32 && K % 32 == 0, where, "K must be a positive multiple of 32");
+    HN_REQUIRE(N >= 64 && N % 64 == 0, where, "N must be a positive multiple of 64");
+    HN_REQUIRE(lda % 4 == 0 && ldc % 4 == 0, where, "row pitches must be multiples of 4 floats");
+    HN_REQUIRE(M < (1ll << 31), where, "M out of range");
+    HN_REQUIRE((((uintptr_t)A | (uintptr_t)W_hi | (uintptr_t)W_lo | (uintptr_t)C | (uintptr_t)bias) & 15) == 0, where,
+               "pointers must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (N % 128 == 0) return launch<128>(A, M, K, lda, W_hi, W_lo, N, bias, C, ldc, st);
+    return launch<64>(A, M, K, lda, W_hi, W_lo, N, bias, C, ldc, st);
+}

@@ -127,6 +127,66 @@ def painn_edge(xh, vec, geom, Wt, bias, offset, g: RowGraph, p):
 
 
 # ----------------------------------------------------------------------------------------------------
+# node-side dense layers on the tensor cores (fused path)
+# ----------------------------------------------------------------------------------------------------
+_SPLIT_CACHE = {}
+
+
+def _split_cached(w: Tensor, transposed: bool):
+    """(hi, lo) TF32 split of a weight (or of its transpose), cached per live tensor object and version (addresses and
+    ids are recycled by the allocator, so the entry keeps a weak reference and is only trusted for the same object)."""
+    import weakref
+    key = (id(w), transposed)
+    hit = _SPLIT_CACHE.get(key)
+    if hit is not None and hit[0]() is w and hit[1] == w._version:
+        return hit[2], hit[3]
+    hi, lo = ops.split_tf32(w.detach().t().contiguous() if transposed else w.detach())
+    if len(_SPLIT_CACHE) > 1024:
+        _SPLIT_CACHE.clear()
+    _SPLIT_CACHE[key] = (weakref.ref(w), w._version, hi, lo)
+    return hi, lo
+
+
+class _LinearTC(Function):
+    """``x @ W^T + b`` through ``hn_gemm_tf32x3`` (tcgen05, 3xTF32).  Backward: the data gradient uses the same kernel
+    with the transposed weight; weight / bias gradients (only when parameters require grad) are plain torch GEMMs."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        hi, lo = _split_cached(weight, False)
+        x2 = x.reshape(-1, x.size(-1))
+        out = ops.gemm_tf32x3(x2, hi, lo, None if bias is None else bias.detach().contiguous())
+        return out.view(tuple(x.shape[:-1]) + (weight.size(0),))
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        gx = gw = gb = None
+        g2 = g.reshape(-1, g.size(-1))
+        if ctx.needs_input_grad[0]:
+            if ops.gemm_supported(weight.size(0), weight.size(1)):
+                hi, lo = _split_cached(weight, True)
+                gx = ops.gemm_tf32x3(g2.contiguous(), hi, lo, None).view(x.shape)
+            else:
+                gx = (g2 @ weight).view(x.shape)
+        if ctx.needs_input_grad[1]:
+            gw = g2.t() @ x.reshape(-1, x.size(-1))
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = g2.sum(0)
+        return gx, gw, gb
+
+
+def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor], tensor_cores: bool) -> Tensor:
+    """nn.Linear forward; on the fused path (fp32, K % 32 == 0, N % 64 == 0) it runs on the tensor cores."""
+    if tensor_cores and x.dtype == torch.float32 and ops.gemm_supported(weight.size(1), weight.size(0)) and x.numel() > 0:
+        return _LinearTC.apply(x, weight, bias)
+    return torch.nn.functional.linear(x, weight, bias)
+
+
+# ----------------------------------------------------------------------------------------------------
 # composite (any-order differentiable) formulation
 # ----------------------------------------------------------------------------------------------------
 def edge_geometry_composite(pos: Tensor, cell: Optional[Tensor], g: RowGraph) -> Tensor:

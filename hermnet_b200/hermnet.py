@@ -61,6 +61,7 @@ class _HermNet(nn.Module):
         self.intensive = intensive
         self.pbc_shift = pbc_shift
         self.edge_path = "auto"       # 'auto' | 'fused' | 'composite'
+        self.tensor_core_linear = True   # fused path: node-side nn.Linear layers run on tcgen05 (3xTF32 split)
         self.store_features = False   # write data.x / data.vec back like the reference does (hermnet.py:63-64)
 
         self.embed = nn.Embedding(len(atomic_numbers), hidden_channels)
@@ -145,7 +146,9 @@ class _HermNet(nn.Module):
             if halo is not None and li > 0:       # layer 0 reads embeddings / zeros, which every rank has locally
                 x, vec = halo.exchange(x, vec)
             x, vec = self._layer(conv, x, vec, geom, g, p)
-        e_atom = self.out_energy(x)                                      # [N,1]   hermnet.py:129
+        tc = fused and self.tensor_core_linear
+        h = self.out_energy[1](Fn.linear(x, self.out_energy[0].weight, self.out_energy[0].bias, tc))
+        e_atom = self.out_energy[2](h)                                   # [N,1]   hermnet.py:129
         sb = g.seg_batch
         energy = Fn.segment_sum(e_atom, sb).squeeze(1)[: g.n_graphs]     # hermnet.py:130 (owned atoms only)
         if self.intensive:
@@ -167,16 +170,20 @@ class _HermNet(nn.Module):
             w1s.append(ml.x_proj[0].weight * ml.x_layernorm.weight[None, :])
             b1s.append(ml.x_proj[0].bias + ml.x_proj[0].weight @ ml.x_layernorm.bias)
         blocks = []
+        tc = p is not None and self.tensor_core_linear
+
+        def lin(t, layer):
+            return Fn.linear(t, layer.weight, layer.bias, tc)
+
         if self.KIND == "HVNet":     # every sub-network reads every row: one [N,F]x[F,M*F] GEMM for the first Linear
-            h = mods[0].message_layer.x_proj[1](torch.addmm(torch.cat(b1s), xhat, torch.cat(w1s, 0).t()))
+            h = mods[0].message_layer.x_proj[1](Fn.linear(xhat, torch.cat(w1s, 0), torch.cat(b1s), tc))
             for m, mod in enumerate(mods):
-                l2 = mod.message_layer.x_proj[2]
-                blocks.append(torch.nn.functional.linear(h[:, m * F:(m + 1) * F], l2.weight, l2.bias))
+                blocks.append(lin(h[:, m * F:(m + 1) * F], mod.message_layer.x_proj[2]))
         else:
             for mod, srcs, w1, b1 in zip(mods, g.xh_sources, w1s, b1s):
                 rows = xhat[srcs[0][0]:srcs[0][1]] if len(srcs) == 1 else torch.cat([xhat[lo:hi] for lo, hi in srcs], 0)
                 ml = mod.message_layer
-                blocks.append(ml.x_proj[2](ml.x_proj[1](torch.addmm(b1, rows, w1.t()))))
+                blocks.append(lin(ml.x_proj[1](Fn.linear(rows, w1, b1, tc)), ml.x_proj[2]))
         xh = torch.cat(blocks, 0)                                        # [rows, 3F]
         Wt = torch.stack([m.message_layer.rbf_proj.weight.t() for m in mods])   # [M,K,3F]
         bias = torch.stack([m.message_layer.rbf_proj.bias for m in mods])       # [M,3F]
@@ -216,7 +223,7 @@ class _HermNet(nn.Module):
                         dxm, dvm, vdot = dx[sl, slots[0]], dvec[sl, slots[0]], None
                     if not g.mod_active_host[m]:                         # hermnet.py:56-57: no edges -> rows stay 0
                         continue
-                    v_new, x_new = mod.node_update(xt, vt, dxm, dvm, vdot)
+                    v_new, x_new = mod.node_update(xt, vt, dxm, dvm, vdot, lin)
                     x_acc = x_new if x_acc is None else x_acc + x_new
                     v_acc = v_new if v_acc is None else v_acc + v_new
                 if x_acc is None:

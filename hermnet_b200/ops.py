@@ -323,3 +323,34 @@ def segment_sum(Y: Tensor, rowptr: Tensor, perm: Optional[Tensor], n_rows: int) 
         _lib.check(lib.hn_segment_sum(_ptr(Y), _ptr(rowptr), _ptr(perm), n_rows, C, _ptr(out), _stream(dev)),
                    "hn_segment_sum")
     return out
+
+
+# ----------------------------------------------------------------------------------------------------
+# tensor-core dense layer (3xTF32 split on tcgen05)
+# ----------------------------------------------------------------------------------------------------
+def split_tf32(w: Tensor) -> Tuple[Tensor, Tensor]:
+    """``w = hi + lo`` with ``hi`` exactly representable in TF32 (low 13 mantissa bits cleared)."""
+    w = w.detach().contiguous()
+    hi = (w.view(torch.int32) & -8192).view(torch.float32)
+    return hi, w - hi
+
+
+def gemm_supported(K: int, N: int) -> bool:
+    return K >= 32 and K % 32 == 0 and N >= 64 and N % 64 == 0
+
+
+def gemm_tf32x3(a: Tensor, w_hi: Tensor, w_lo: Tensor, bias: Optional[Tensor]) -> Tensor:
+    """``a [M,K] @ (w_hi + w_lo)[N,K]^T + bias`` on the tensor cores; ``a`` may be a column slice (row pitch)."""
+    lib = _lib.load()
+    if a.dim() != 2 or a.stride(1) != 1 or a.stride(0) % 4 != 0 or a.data_ptr() % 16 != 0:
+        a = a.contiguous()
+    dev = _chk("gemm_tf32x3", w_hi, w_lo, bias)
+    require_cuda(a, "gemm_tf32x3")
+    _f32("gemm_tf32x3", a, w_hi, w_lo, bias)
+    M, K = a.shape
+    N = w_hi.size(0)
+    out = torch.empty((M, N), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev), _timed("gemm_tf32x3", dev):
+        _lib.check(lib.hn_gemm_tf32x3(_ptr(a), M, K, a.stride(0), _ptr(w_hi), _ptr(w_lo), N, _ptr(bias), _ptr(out), N,
+                                      _stream(dev)), "hn_gemm_tf32x3")
+    return out

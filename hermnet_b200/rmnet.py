@@ -59,13 +59,17 @@ class PaiNNUpdate(nn.Module):
         self.inv_sqrt_2 = 1 / math.sqrt(2.0)
         self.inv_sqrt_h = 1 / math.sqrt(hidden_channels)
 
-    def forward(self, x, vec, vdot=None):
+    def forward(self, x, vec, vdot=None, lin=None):
+        """``lin(input, nn.Linear)`` lets the model route the dense layers to the tensor-core GEMM."""
+        if lin is None:
+            lin = lambda t, layer: layer(t)
         F = self.hidden_channels
-        v1, v2 = torch.split(self.vec_proj(vec), F, dim=-1)
+        v1, v2 = torch.split(lin(vec, self.vec_proj), F, dim=-1)
         if vdot is None:
             vdot = (v1 * v2).sum(dim=1) * self.inv_sqrt_h
         vnorm = torch.sqrt(torch.sum(v2 ** 2, dim=-2) + 1e-8)
-        a1, a2, a3 = torch.split(self.xvec_proj(torch.cat([x, vnorm], dim=-1)), F, dim=-1)
+        h = self.xvec_proj[1](lin(torch.cat([x, vnorm], dim=-1), self.xvec_proj[0]))
+        a1, a2, a3 = torch.split(lin(h, self.xvec_proj[2]), F, dim=-1)
         return (a1 + a2 * vdot) * self.inv_sqrt_2, a3.unsqueeze(1) * v1
 
 
@@ -79,11 +83,11 @@ class PaiNNModule(nn.Module):
         self.update_layer = PaiNNUpdate(hidden_channels)
         self.inv_sqrt_2 = 1 / math.sqrt(2.0)
 
-    def node_update(self, x, vec, dx, dvec, vdot=None):
+    def node_update(self, x, vec, dx, dvec, vdot=None, lin=None):
         """rmnet.py:24-32 on the rows of one sub-network: residual, rescale, update block.  Returns (vec, x)."""
         x = (x + dx) * self.inv_sqrt_2
         vec = vec + dvec
-        dx2, dvec2 = self.update_layer(x, vec, vdot)
+        dx2, dvec2 = self.update_layer(x, vec, vdot, lin)
         return vec + dvec2, x + dx2
 
 

@@ -171,6 +171,17 @@ int hn_gather_rows(const float *X, const int32_t *idx, int64_t n_out, int32_t C,
 int hn_segment_sum(const float *Y, const int32_t *rowptr, const int32_t *perm, int32_t n_rows, int32_t C,
                    float *out, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Node-side dense layers on the tcgen05 tensor cores (3xTF32 split, fp32-class accuracy):
+ *   C[M,N] (row pitch ldc) = A[M,K] (row pitch lda) . W[N,K]^T + bias[N]   (bias may be NULL)
+ * Replaces the cuBLAS fp32 GEMMs behind nn.Linear in HermNet/rmnet.py:40-49 (x_proj), :84-89
+ * (vec_proj, xvec_proj) and hermnet.py:112-116 (out_energy) on the fused path.  W is passed
+ * pre-split: W_hi = W & 0xFFFFE000 (bitwise), W_lo = W - W_hi.  K % 32 == 0, N % 64 == 0,
+ * pitches % 4 == 0, 16-byte aligned pointers.
+ * ------------------------------------------------------------------------------------------- */
+int hn_gemm_tf32x3(const float *A, int64_t M, int64_t K, int64_t lda, const float *W_hi, const float *W_lo,
+                   int64_t N, const float *bias, float *C, int64_t ldc, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -236,11 +236,22 @@ def segment_sum(Y, rowptr, perm, n_rows):
     return torch.zeros((n_rows, Y.size(1)), dtype=Y.dtype).index_add_(0, row, Y[items])
 
 
+def gemm_tf32x3(a, w_hi, w_lo, bias):
+    out = a @ (w_hi + w_lo).t()
+    return out if bias is None else out + bias
+
+
+def split_tf32(w):
+    w = w.detach().contiguous()
+    hi = (w.view(torch.int32) & -8192).view(torch.float32)
+    return hi, w - hi
+
+
 def install(monkeypatch):
     """Swap ``hermnet_b200.ops`` for the CPU emulation (pytest ``monkeypatch`` restores it afterwards)."""
     for name in ("radius_graph", "sort_by_key", "expand_rowptr", "triplets", "triplet_dots", "edge_geom_fwd",
                  "edge_geom_bwd", "edge_params", "edge_num_slices", "painn_edge_fwd", "painn_edge_bwd_dst",
-                 "painn_edge_bwd_src", "painn_edge_bwd_w", "gather_rows", "segment_sum"):
+                 "painn_edge_bwd_src", "painn_edge_bwd_w", "gather_rows", "segment_sum", "gemm_tf32x3", "split_tf32"):
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(ops, "require_cuda", lambda t, what: None)
     monkeypatch.setattr(ops, "compute_device", lambda t: t.device)
