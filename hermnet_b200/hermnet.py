@@ -72,7 +72,7 @@ class _HermNet(nn.Module):
                                                   for name in self.module_names()}))
         self.out_energy = nn.Sequential(nn.Linear(hidden_channels, hidden_channels // 2), ScaledSiLU(),
                                         nn.Linear(hidden_channels // 2, 1))
-        self.builder = GraphBuilder(self.KIND, self.elems, self.rc, pbc_shift)
+        self.builder = GraphBuilder(self.KIND, self.elems, self.rc, pbc_shift, num_rbf=num_rbf, hidden=hidden_channels)
 
     # ------------------------------------------------------------------------------------------------
     def module_names(self) -> List[str]:
