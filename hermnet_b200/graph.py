@@ -16,6 +16,7 @@ Row layouts (``rows_per_atom`` rows per destination atom, ``row_mod`` = weight-s
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
@@ -258,7 +259,9 @@ class GraphBuilder:
     def __init__(self, kind: str, elems: Sequence[str], rc: float, pbc_shift: str = "reference",
                  num_rbf: Optional[int] = None, hidden: Optional[int] = None):
         self.num_rbf, self.hidden = num_rbf, hidden     # set: also build the TilePlans of the tiled edge kernels
-        self.tile_plans = True
+        # (environment switches: A/B measurements only)
+        self.tile_plans = os.environ.get("HERMNET_B200_TILED", "0") != "0"
+        self.spatial_sort = os.environ.get("HERMNET_B200_SPATIAL", "1") != "0"   # Morton order inside every type slice
         if kind not in ("HVNet", "HPNet", "HTNet"):
             raise ValueError(kind)
         if pbc_shift not in ("reference", "physical"):
@@ -285,15 +288,44 @@ class GraphBuilder:
         return self._z2t[dev]
 
     # ---------------------------------------------------------------------------------------------------
-    def _order(self, Z: Tensor, owned: Optional[Tensor] = None):
-        """Internal order: by element type, owned atoms before ghost atoms inside a type."""
-        types = self.z2t(Z.device)[Z.long()]
-        if owned is None:
-            types_sorted, perm = torch.sort(types, stable=True)
-            key_sorted = types_sorted.long() * 2
+    @staticmethod
+    def _morton(pos: Tensor, cell: Optional[Tensor], batch: Optional[Tensor]) -> Tensor:
+        """30-bit Morton (Z-order) code of every atom: 10 bits per axis of the fractional (periodic) or bounding-box
+        (open) coordinate.  Only used as a sort key, so that atoms that are close in space are close in memory and the
+        feature rows gathered by neighbouring destination rows share L2 lines."""
+        p = pos.detach().to(torch.float32)
+        if cell is not None:
+            c = cell.detach().to(torch.float32).reshape(-1, 3, 3)
+            inv = torch.linalg.inv(c)
+            f = torch.einsum("ni,nij->nj", p, inv[batch.long()] if (batch is not None and c.size(0) > 1) else
+                             inv[:1].expand(p.size(0), 3, 3))
+            f = f - torch.floor(f)
         else:
-            key_sorted, perm = torch.sort(types.long() * 2 + (~owned).long(), stable=True)
-            types_sorted = torch.div(key_sorted, 2, rounding_mode="floor")
+            lo = p.min(0).values if p.numel() else p.new_zeros(3)
+            span = ((p.max(0).values - lo) if p.numel() else p.new_ones(3)).clamp(min=1e-6)
+            f = (p - lo) / (span * 1.0001)
+        q = (f * 1024.0).long().clamp_(0, 1023)
+
+        def spread(v):      # 10 bits -> every third bit
+            v = (v | (v << 16)) & 0x030000FF
+            v = (v | (v << 8)) & 0x0300F00F
+            v = (v | (v << 4)) & 0x030C30C3
+            v = (v | (v << 2)) & 0x09249249
+            return v
+
+        return spread(q[:, 0]) | (spread(q[:, 1]) << 1) | (spread(q[:, 2]) << 2)
+
+    def _order(self, Z: Tensor, owned: Optional[Tensor] = None, pos: Optional[Tensor] = None,
+               cell: Optional[Tensor] = None, batch: Optional[Tensor] = None):
+        """Internal order: by element type, owned atoms before ghost atoms inside a type, Morton order inside that."""
+        types = self.z2t(Z.device)[Z.long()]
+        major = types.long() * 2 + (0 if owned is None else (~owned).long())
+        if pos is not None and self.spatial_sort and Z.numel() > 0:
+            key_sorted, perm = torch.sort((major << 30) | self._morton(pos, cell, batch), stable=True)
+            key_sorted = key_sorted >> 30
+        else:
+            key_sorted, perm = torch.sort(major, stable=True)
+        types_sorted = torch.div(key_sorted, 2, rounding_mode="floor")
         counts = torch.bincount(key_sorted, minlength=2 * (self.T + 1)).view(-1, 2)
         c = counts.tolist()                                          # one host sync per graph build
         type_ptr = [0]
@@ -310,7 +342,7 @@ class GraphBuilder:
         dev = pos.device
         n = pos.size(0)
         n_graphs = 1 if batch is None else (int(batch.max().item()) + 1 if n else 1)
-        types, perm, inv, type_ptr = self._order(Z)
+        types, perm, inv, type_ptr = self._order(Z, None, pos, cell, batch)
         pos32 = pos.detach().to(torch.float32)
         cell32 = None if cell is None else cell.detach().to(torch.float32).reshape(-1, 3, 3).contiguous()
         if cell32 is None and max_neighbors == 0:
@@ -336,7 +368,7 @@ class GraphBuilder:
         periodic ``cell``; rows are kept for owned destinations only, every local atom may be a source."""
         dev = pos.device
         n = pos.size(0)
-        types, perm, inv, type_ptr = self._order(Z, owned)
+        types, perm, inv, type_ptr = self._order(Z, owned, pos, cell, None)
         own_count = list(self._own_count)
         pos32 = pos.detach().to(torch.float32)
         cell32 = cell.detach().to(torch.float32).reshape(-1, 3, 3).contiguous()
@@ -369,7 +401,7 @@ class GraphBuilder:
     def from_coo(self, n: int, src: Tensor, dst: Tensor, shift: Optional[Tensor], Z: Tensor, batch: Optional[Tensor],
                  order=None, pos: Optional[Tensor] = None, cell: Optional[Tensor] = None) -> RowGraph:
         dev = Z.device
-        types, perm, inv, type_ptr = order if order is not None else self._order(Z)
+        types, perm, inv, type_ptr = order if order is not None else self._order(Z, None, pos, cell, batch)
         n_graphs = 1 if batch is None else (int(batch.max().item()) + 1 if n else 1)
         src_i, dst_i = inv[src], inv[dst]
         G = self.n_groups

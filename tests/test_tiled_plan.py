@@ -28,6 +28,7 @@ def _model(kind, elems, F, K, dev, layers=2, seed=7):
     m = getattr(H, kind)(elems=elems, rc=5.0, num_layers=layers, hidden_channels=F, num_rbf=K).to(dev).eval()
     for p in m.parameters():
         p.requires_grad_(False)
+    m.builder.tile_plans = True     # opt-in while the row kernels are still as fast (HERMNET_B200_TILED=1)
     return m
 
 
