@@ -48,6 +48,13 @@ SIGNATURES = {
     "hn_painn_edge_bwd_dst_tiled": (c_int32, [POINTER(EdgeParams)] + [P] * 7 + [c_int32, c_int32] + [P] * 6 + [c_int64, P]),
     "hn_painn_edge_bwd_src_tiled": (c_int32, [POINTER(EdgeParams)] + [P] * 5 + [c_int32, c_int32] + [P] * 8),
     "hn_gemm_tf32x3": (c_int32, [P, c_int64, c_int64, c_int64, P, P, c_int64, P, P, c_int64, P]),
+    "hn_gemm_tf32x3_ex": (c_int32, [P, c_int64, c_int64, c_int64, P, P, c_int64, P, P, c_int64, c_int32, P, c_int64, P, c_int64, P]),
+    "hn_node_pre": (c_int32, [c_int64, c_int32, P, P, c_int64, P, P, c_int64, P, P, P]),
+    "hn_node_mid": (c_int32, [c_int64, c_int32, P, P, P, P]),
+    "hn_node_post": (c_int32, [c_int64, c_int32, P, P, P, P, P, P, P, P]),
+    "hn_node_post_bwd": (c_int32, [c_int64, c_int32, P, P, P, P, P, P, P, P, P]),
+    "hn_node_mid_bwd": (c_int32, [c_int64, c_int32, P, P, P, P, c_int64, P, P]),
+    "hn_node_pre_bwd": (c_int32, [c_int64, c_int32, P, P, P, P, P, P, P]),
     "hn_gather_rows": (c_int32, [P, P, c_int64, c_int32, P, P]),
     "hn_segment_sum": (c_int32, [P, P, P, c_int32, c_int32, P, P]),
 }

@@ -71,6 +71,12 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
+__device__ __forceinline__ float ssilu(float z) { return z / (1.f + expf(-z)) * (1.f / 0.6f); }
+__device__ __forceinline__ float dssilu(float z) {
+    const float sg = 1.f / (1.f + expf(-z));
+    return sg * (1.f + z * (1.f - sg)) * (1.f / 0.6f);
+}
+
 template <int BN>
 struct Smem {
     static constexpr int kA = BM * BK * 4;   // 16 KB
@@ -84,7 +90,8 @@ template <int BN>
 __global__ void __launch_bounds__(256, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                    const __grid_constant__ CUtensorMap tmBlo, const float *__restrict__ bias, float *__restrict__ C,
-                   int M, int N, int K, long long ldc) {
+                   int M, int N, int K, long long ldc, int mode, const float *__restrict__ aux, long long ld_aux,
+                   float *__restrict__ C2, long long ldc2) {
     extern __shared__ uint8_t smem_raw[];
     using L = Smem<BN>;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -203,6 +210,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         const float4 b = __ldg(reinterpret_cast<const float4 *>(bias + n0 + c0 + j));
                         o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
                     }
+                    if (mode == 1) {          // C2 = pre-activation (optional), C = ScaledSiLU(pre)   (rmnet.py:110-117)
+                        if (C2 != nullptr) *reinterpret_cast<float4 *>(C2 + row * ldc2 + n0 + c0 + j) = o;
+                        o.x = ssilu(o.x); o.y = ssilu(o.y); o.z = ssilu(o.z); o.w = ssilu(o.w);
+                    } else if (mode == 2) {   // C = acc * ScaledSiLU'(aux): backward through the activation
+                        const float4 z = __ldg(reinterpret_cast<const float4 *>(aux + row * ld_aux + n0 + c0 + j));
+                        o.x *= dssilu(z.x); o.y *= dssilu(z.y); o.z *= dssilu(z.z); o.w *= dssilu(z.w);
+                    }
                     *reinterpret_cast<float4 *>(dst + j) = o;
                 }
             }
@@ -248,7 +262,7 @@ int make_map(CUtensorMap *map, const float *ptr, int64_t rows, int64_t K, int64_
 
 template <int BN>
 int launch(const float *A, int64_t M, int64_t K, int64_t lda, const float *Whi, const float *Wlo, int64_t N, const float *bias,
-           float *C, int64_t ldc, cudaStream_t st) {
+           float *C, int64_t ldc, int mode, const float *aux, int64_t ld_aux, float *C2, int64_t ldc2, cudaStream_t st) {
     const char *where = "hn_gemm_tf32x3";
     CUtensorMap ta, tbh, tbl;
     HN_REQUIRE(make_map(&ta, A, M, K, lda, BM) == 0, where, "cuTensorMapEncodeTiled failed for A");
@@ -260,25 +274,36 @@ int launch(const float *A, int64_t M, int64_t K, int64_t lda, const float *Whi, 
         attr_set = true;
     }
     dim3 grid((unsigned)(N / BN), (unsigned)((M + BM - 1) / BM));
-    gemm_tf32x3_kernel<BN><<<grid, 256, Smem<BN>::kTotal, st>>>(ta, tbh, tbl, bias, C, (int)M, (int)N, (int)K, (long long)ldc);
+    gemm_tf32x3_kernel<BN><<<grid, 256, Smem<BN>::kTotal, st>>>(ta, tbh, tbl, bias, C, (int)M, (int)N, (int)K, (long long)ldc, mode, aux,
+                                                                 (long long)ld_aux, C2, (long long)ldc2);
     return hn::check_launch(where);
 }
 
 }  // namespace
 
-// C[M,N] (row pitch ldc) = A[M,K] (row pitch lda) . W[N,K]^T + bias;  W given pre-split (hi = W & 0xFFFFE000, lo = W - hi).
-// Requirements: K % 32 == 0, N % 64 == 0, lda % 4 == 0, 16-byte aligned pointers.
-extern "C" int hn_gemm_tf32x3(const float *A, int64_t M, int64_t K, int64_t lda, const float *W_hi, const float *W_lo, int64_t N,
-                              const float *bias, float *C, int64_t ldc, void *stream) {
+// C[M,N] (row pitch ldc) = epilogue(A[M,K] (row pitch lda) . W[N,K]^T + bias);  W given pre-split (hi = W & 0xFFFFE000, lo = W - hi).
+//   mode 0: identity            mode 1: C = ScaledSiLU(pre), C2 = pre (optional, row pitch ldc2)
+//   mode 2: C = (A.W^T) * ScaledSiLU'(aux[row][col])  (aux row pitch ld_aux) -- the backward pass through the activation
+// Requirements: K % 32 == 0, N % 64 == 0, row pitches % 4 == 0, 16-byte aligned pointers.
+extern "C" int hn_gemm_tf32x3_ex(const float *A, int64_t M, int64_t K, int64_t lda, const float *W_hi, const float *W_lo, int64_t N,
+                                 const float *bias, float *C, int64_t ldc, int32_t mode, const float *aux, int64_t ld_aux,
+                                 float *C2, int64_t ldc2, void *stream) {
     const char *where = "hn_gemm_tf32x3";
     if (M <= 0) return 0;
     HN_REQUIRE(K >= 32 && K % 32 == 0, where, "K must be a positive multiple of 32");
     HN_REQUIRE(N >= 64 && N % 64 == 0, where, "N must be a positive multiple of 64");
-    HN_REQUIRE(lda % 4 == 0 && ldc % 4 == 0, where, "row pitches must be multiples of 4 floats");
+    HN_REQUIRE(lda % 4 == 0 && ldc % 4 == 0 && ld_aux % 4 == 0 && ldc2 % 4 == 0, where, "row pitches must be multiples of 4 floats");
     HN_REQUIRE(M < (1ll << 31), where, "M out of range");
-    HN_REQUIRE((((uintptr_t)A | (uintptr_t)W_hi | (uintptr_t)W_lo | (uintptr_t)C | (uintptr_t)bias) & 15) == 0, where,
-               "pointers must be 16-byte aligned");
+    HN_REQUIRE(mode >= 0 && mode <= 2, where, "unknown epilogue mode");
+    HN_REQUIRE(mode != 2 || aux != nullptr, where, "mode 2 needs the pre-activation (aux)");
+    HN_REQUIRE((((uintptr_t)A | (uintptr_t)W_hi | (uintptr_t)W_lo | (uintptr_t)C | (uintptr_t)bias | (uintptr_t)aux | (uintptr_t)C2) & 15) == 0,
+               where, "pointers must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    if (N % 128 == 0) return launch<128>(A, M, K, lda, W_hi, W_lo, N, bias, C, ldc, st);
-    return launch<64>(A, M, K, lda, W_hi, W_lo, N, bias, C, ldc, st);
+    if (N % 128 == 0) return launch<128>(A, M, K, lda, W_hi, W_lo, N, bias, C, ldc, mode, aux, ld_aux, C2, ldc2, st);
+    return launch<64>(A, M, K, lda, W_hi, W_lo, N, bias, C, ldc, mode, aux, ld_aux, C2, ldc2, st);
+}
+
+extern "C" int hn_gemm_tf32x3(const float *A, int64_t M, int64_t K, int64_t lda, const float *W_hi, const float *W_lo, int64_t N,
+                              const float *bias, float *C, int64_t ldc, void *stream) {
+    return hn_gemm_tf32x3_ex(A, M, K, lda, W_hi, W_lo, N, bias, C, ldc, 0, nullptr, 4, nullptr, 4, stream);
 }

@@ -1,0 +1,177 @@
+// Fused element-wise stages of the node-side update block (HermNet/rmnet.py:21-32 PaiNNModule.forward residuals and
+// rmnet.py:94-107 PaiNNUpdate.forward), forward and hand-written backward.  The dense layers between the stages run on
+// the tensor cores (hn_gemm.cu); these kernels replace ~20 separate element-wise launches per sub-network and
+// direction with three, each one streaming pass over its operands (HBM-bound, float4 accesses, thread = 4 channels).
+//
+//   pre :  x' = (x + dx)/sqrt(2) -> xcat[:, 0:F]          vec' = vec + dvec                        rmnet.py:24-26
+//   mid :  [v1 v2] = vec'.Wv^T (GEMM)   vdot = sum_k v1.v2/sqrt(F)   vn = sqrt(sum_k v2^2 + 1e-8) -> xcat[:, F:2F]
+//   post:  [a1 a2 a3] = MLP(xcat) (GEMMs)   x'' = x' + (a1 + a2*vdot)/sqrt(2)   vec'' = vec' + a3*v1      rmnet.py:28-32
+#include "hn_common.cuh"
+
+namespace {
+
+constexpr float kInvSqrt2 = 0.70710678118654752440f;
+
+__device__ __forceinline__ float4 ld4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ void st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 mul4(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+__device__ __forceinline__ float4 scl4(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+__device__ __forceinline__ float4 fma4(float4 a, float4 b, float4 c) {
+    return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w));
+}
+
+// one thread = 4 consecutive channels of one row
+#define HN_ROW_CH(n, F)                                                              \
+    const long long t_ = (long long)blockIdx.x * blockDim.x + threadIdx.x;           \
+    const int q_ = (F) >> 2;                                                         \
+    const long long r = t_ / q_;                                                     \
+    if (r >= (n)) return;                                                            \
+    const int c = (int)(t_ - r * q_) << 2;
+
+__global__ void node_pre_kernel(long long n, int F, const float *__restrict__ x, const float *__restrict__ dx, long long ld_dx,
+                                const float *__restrict__ vec, const float *__restrict__ dvec, long long ld_dvec,
+                                float *__restrict__ xcat, float *__restrict__ vecp) {
+    HN_ROW_CH(n, F)
+    st4(xcat + r * 2 * F + c, scl4(add4(ld4(x + r * F + c), ld4(dx + r * ld_dx + c)), kInvSqrt2));
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+        st4(vecp + (r * 3 + k) * F + c, add4(ld4(vec + (r * 3 + k) * F + c), ld4(dvec + r * ld_dvec + (long long)k * F + c)));
+}
+
+__global__ void node_mid_kernel(long long n, int F, const float *__restrict__ v12, float *__restrict__ vdot,
+                                float *__restrict__ xcat) {
+    HN_ROW_CH(n, F)
+    const float cF = 1.0f / sqrtf((float)F);
+    float4 dot = make_float4(0.f, 0.f, 0.f, 0.f), nn = make_float4(1e-8f, 1e-8f, 1e-8f, 1e-8f);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float4 v1 = ld4(v12 + (r * 3 + k) * 2 * F + c), v2 = ld4(v12 + (r * 3 + k) * 2 * F + F + c);
+        dot = fma4(v1, v2, dot);
+        nn = fma4(v2, v2, nn);
+    }
+    st4(vdot + r * F + c, scl4(dot, cF));
+    st4(xcat + r * 2 * F + F + c, make_float4(sqrtf(nn.x), sqrtf(nn.y), sqrtf(nn.z), sqrtf(nn.w)));
+}
+
+__global__ void node_post_kernel(long long n, int F, const float *__restrict__ xcat, const float *__restrict__ a,
+                                 const float *__restrict__ vdot, const float *__restrict__ vecp, const float *__restrict__ v12,
+                                 float *__restrict__ x_out, float *__restrict__ vec_out) {
+    HN_ROW_CH(n, F)
+    const float4 a1 = ld4(a + r * 3 * F + c), a2 = ld4(a + r * 3 * F + F + c), a3 = ld4(a + r * 3 * F + 2 * F + c);
+    st4(x_out + r * F + c, add4(ld4(xcat + r * 2 * F + c), scl4(fma4(a2, ld4(vdot + r * F + c), a1), kInvSqrt2)));
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+        st4(vec_out + (r * 3 + k) * F + c, fma4(a3, ld4(v12 + (r * 3 + k) * 2 * F + c), ld4(vecp + (r * 3 + k) * F + c)));
+}
+
+// backward of post: g_a = (g_x/sqrt2, g_x*vdot/sqrt2, sum_k g_vec[k]*v1[k]); g_vdot = g_x*a2/sqrt2; g_v12[.., 0:F] = g_vec*a3
+__global__ void node_post_bwd_kernel(long long n, int F, const float *__restrict__ g_x, const float *__restrict__ g_vec,
+                                     const float *__restrict__ a, const float *__restrict__ vdot, const float *__restrict__ v12,
+                                     float *__restrict__ g_a, float *__restrict__ g_vdot, float *__restrict__ g_v12) {
+    HN_ROW_CH(n, F)
+    const float4 gx = scl4(ld4(g_x + r * F + c), kInvSqrt2);
+    const float4 a2 = ld4(a + r * 3 * F + F + c), a3 = ld4(a + r * 3 * F + 2 * F + c);
+    float4 ga3 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float4 gv = ld4(g_vec + (r * 3 + k) * F + c);
+        ga3 = fma4(gv, ld4(v12 + (r * 3 + k) * 2 * F + c), ga3);
+        st4(g_v12 + (r * 3 + k) * 2 * F + c, mul4(gv, a3));
+    }
+    st4(g_a + r * 3 * F + c, gx);
+    st4(g_a + r * 3 * F + F + c, mul4(gx, ld4(vdot + r * F + c)));
+    st4(g_a + r * 3 * F + 2 * F + c, ga3);
+    st4(g_vdot + r * F + c, mul4(gx, a2));
+}
+
+// backward of mid: g_v1 += g_vdot*v2/sqrt(F);  g_v2 = g_vn*v2/vn + g_vdot*v1/sqrt(F)      (g_vn = g_cat[:, F:2F])
+__global__ void node_mid_bwd_kernel(long long n, int F, const float *__restrict__ g_vdot, const float *__restrict__ g_cat,
+                                    const float *__restrict__ v12, const float *__restrict__ vn, long long ld_vn, float *__restrict__ g_v12) {
+    HN_ROW_CH(n, F)
+    const float cF = 1.0f / sqrtf((float)F);
+    const float4 gd = scl4(ld4(g_vdot + r * F + c), cF);
+    const float4 gn = ld4(g_cat + r * 2 * F + F + c), nn = ld4(vn + r * ld_vn + c);
+    const float4 gnn = make_float4(gn.x / nn.x, gn.y / nn.y, gn.z / nn.z, gn.w / nn.w);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const long long o = (r * 3 + k) * 2 * F + c;
+        const float4 v1 = ld4(v12 + o), v2 = ld4(v12 + o + F);
+        st4(g_v12 + o, fma4(gd, v2, ld4(g_v12 + o)));
+        st4(g_v12 + o + F, fma4(gnn, v2, mul4(gd, v1)));
+    }
+}
+
+// backward of pre: g_x = g_dx = (g_xn + g_cat[:, 0:F])/sqrt(2);  g_vec = g_dvec = g_vecn + g_vecp
+__global__ void node_pre_bwd_kernel(long long n, int F, const float *__restrict__ g_xn, const float *__restrict__ g_cat,
+                                    const float *__restrict__ g_vecn, const float *__restrict__ g_vecp, float *__restrict__ g_x,
+                                    float *__restrict__ g_vec) {
+    HN_ROW_CH(n, F)
+    st4(g_x + r * F + c, scl4(add4(ld4(g_xn + r * F + c), ld4(g_cat + r * 2 * F + c)), kInvSqrt2));
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+        st4(g_vec + (r * 3 + k) * F + c, add4(ld4(g_vecn + (r * 3 + k) * F + c), ld4(g_vecp + (r * 3 + k) * F + c)));
+}
+
+inline unsigned blocks_for(long long n, int F) { return (unsigned)((n * (F >> 2) + 255) / 256); }
+
+int check_node(const char *where, long long n, int F) {
+    HN_REQUIRE(F > 0 && F % 4 == 0, where, "hidden_channels must be a multiple of 4");
+    HN_REQUIRE(n >= 0 && n * (long long)(F >> 2) < (1ll << 39), where, "row count out of range");
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int hn_node_pre(int64_t n, int32_t F, const float *x, const float *dx, int64_t ld_dx, const float *vec, const float *dvec,
+                           int64_t ld_dvec, float *xcat, float *vecp, void *stream) {
+    const char *where = "hn_node_pre";
+    if (int rc = check_node(where, n, F)) return rc;
+    if (n == 0) return 0;
+    node_pre_kernel<<<blocks_for(n, F), 256, 0, (cudaStream_t)stream>>>(n, F, x, dx, ld_dx, vec, dvec, ld_dvec, xcat, vecp);
+    return hn::check_launch(where);
+}
+
+extern "C" int hn_node_mid(int64_t n, int32_t F, const float *v12, float *vdot, float *xcat, void *stream) {
+    const char *where = "hn_node_mid";
+    if (int rc = check_node(where, n, F)) return rc;
+    if (n == 0) return 0;
+    node_mid_kernel<<<blocks_for(n, F), 256, 0, (cudaStream_t)stream>>>(n, F, v12, vdot, xcat);
+    return hn::check_launch(where);
+}
+
+extern "C" int hn_node_post(int64_t n, int32_t F, const float *xcat, const float *a, const float *vdot, const float *vecp,
+                            const float *v12, float *x_out, float *vec_out, void *stream) {
+    const char *where = "hn_node_post";
+    if (int rc = check_node(where, n, F)) return rc;
+    if (n == 0) return 0;
+    node_post_kernel<<<blocks_for(n, F), 256, 0, (cudaStream_t)stream>>>(n, F, xcat, a, vdot, vecp, v12, x_out, vec_out);
+    return hn::check_launch(where);
+}
+
+extern "C" int hn_node_post_bwd(int64_t n, int32_t F, const float *g_x, const float *g_vec, const float *a, const float *vdot,
+                                const float *v12, float *g_a, float *g_vdot, float *g_v12, void *stream) {
+    const char *where = "hn_node_post_bwd";
+    if (int rc = check_node(where, n, F)) return rc;
+    if (n == 0) return 0;
+    node_post_bwd_kernel<<<blocks_for(n, F), 256, 0, (cudaStream_t)stream>>>(n, F, g_x, g_vec, a, vdot, v12, g_a, g_vdot, g_v12);
+    return hn::check_launch(where);
+}
+
+extern "C" int hn_node_mid_bwd(int64_t n, int32_t F, const float *g_vdot, const float *g_cat, const float *v12, const float *vn,
+                               int64_t ld_vn, float *g_v12, void *stream) {
+    const char *where = "hn_node_mid_bwd";
+    if (int rc = check_node(where, n, F)) return rc;
+    if (n == 0) return 0;
+    node_mid_bwd_kernel<<<blocks_for(n, F), 256, 0, (cudaStream_t)stream>>>(n, F, g_vdot, g_cat, v12, vn, ld_vn, g_v12);
+    return hn::check_launch(where);
+}
+
+extern "C" int hn_node_pre_bwd(int64_t n, int32_t F, const float *g_xn, const float *g_cat, const float *g_vecn, const float *g_vecp,
+                               float *g_x, float *g_vec, void *stream) {
+    const char *where = "hn_node_pre_bwd";
+    if (int rc = check_node(where, n, F)) return rc;
+    if (n == 0) return 0;
+    node_pre_bwd_kernel<<<blocks_for(n, F), 256, 0, (cudaStream_t)stream>>>(n, F, g_xn, g_cat, g_vecn, g_vecp, g_x, g_vec);
+    return hn::check_launch(where);
+}

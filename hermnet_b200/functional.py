@@ -215,6 +215,141 @@ def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor], tensor_cores: bool
 
 
 # ----------------------------------------------------------------------------------------------------
+# fused node side of one HVNet layer (frozen parameters): two autograd nodes per layer instead of ~60
+# ----------------------------------------------------------------------------------------------------
+def node_fusable(hidden: int) -> bool:
+    """The fused node path chains tensor-core GEMMs with K, N in {F, 2F, 3F, T*F}: needs F % 64 == 0."""
+    return hidden % 64 == 0
+
+
+def _wsplit(w: Tensor, transposed: bool = False):
+    return _split_cached(w, transposed)
+
+
+class _XProjHV(Function):
+    """``xh[m] = x_proj_m(LayerNorm_m(x))`` for every sub-network m of an HVNet layer (rmnet.py:52 run per element,
+    hermnet.py:51-59), written straight into the flat ``[M*N, 3F]`` buffer the edge kernel reads.  The normalisation is
+    computed once (its affine part folded into the first Linear of every sub-network), the first Linears of all
+    sub-networks are one GEMM with the ScaledSiLU in its epilogue, and the backward is hand-written."""
+
+    @staticmethod
+    def forward(ctx, x, mods, eps):
+        N, F = x.shape
+        M = len(mods)
+        xhat, mean, rstd = torch.native_layer_norm(x, (F,), None, None, eps)
+        w1 = torch.cat([m.x_proj[0].weight * m.x_layernorm.weight[None, :] for m in mods], 0).detach()
+        b1 = torch.cat([m.x_proj[0].bias + m.x_proj[0].weight @ m.x_layernorm.bias for m in mods]).detach().contiguous()
+        w1_hi, w1_lo = ops.split_tf32(w1)
+        hpre = torch.empty((N, M * F), dtype=x.dtype, device=x.device)
+        h = torch.empty_like(hpre)
+        ops.gemm_tf32x3_ex(xhat, w1_hi, w1_lo, b1, out=h, mode=1, out2=hpre)
+        xh = torch.empty((M * N, 3 * F), dtype=x.dtype, device=x.device)
+        for m, mod in enumerate(mods):
+            hi, lo = _wsplit(mod.x_proj[2].weight)
+            ops.gemm_tf32x3_ex(h[:, m * F:(m + 1) * F], hi, lo, mod.x_proj[2].bias.detach(), out=xh[m * N:(m + 1) * N])
+        ctx.mods, ctx.w1 = mods, w1
+        ctx.save_for_backward(x, mean, rstd, hpre)
+        return xh
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_xh):
+        x, mean, rstd, hpre = ctx.saved_tensors
+        mods = ctx.mods
+        N, F = x.shape
+        g_xh = g_xh.contiguous()
+        g_pre = torch.empty_like(hpre)
+        for m, mod in enumerate(mods):
+            hi, lo = _wsplit(mod.x_proj[2].weight, True)                      # [F, 3F]: g_h = g_xh . W2
+            ops.gemm_tf32x3_ex(g_xh[m * N:(m + 1) * N], hi, lo, None, out=g_pre[:, m * F:(m + 1) * F], mode=2,
+                               aux=hpre[:, m * F:(m + 1) * F])
+        hi, lo = ops.split_tf32(ctx.w1.t().contiguous())                      # [F, M*F]
+        g_xhat = ops.gemm_tf32x3_ex(g_pre, hi, lo, None)
+        g_x = torch.ops.aten.native_layer_norm_backward(g_xhat, x, [F], mean, rstd, None, None, [True, False, False])[0]
+        return g_x, None, None
+
+
+def xproj_hv(x: Tensor, mods, eps: float) -> Tensor:
+    return _XProjHV.apply(x, mods, eps)
+
+
+class _NodeUpdateHV(Function):
+    """Residual + update block of every sub-network of an HVNet layer on its own destination rows (rmnet.py:24-32,
+    94-107; hermnet.py:60-61 keeps only those rows): three fused element-wise kernels and three tensor-core GEMMs per
+    element forward, the mirror image backward.  Rows of elements without an active sub-network, of unknown elements and
+    ghost rows stay zero (hermnet.py:56-57)."""
+
+    @staticmethod
+    def forward(ctx, x, vec, dx, dvec, g: RowGraph, mods):
+        N, F = x.shape
+        x, vec = x.contiguous(), vec.contiguous()
+        dx2, dvec2 = dx.reshape(N, F), dvec.reshape(N, 3 * F)
+        T = len(mods)
+        covered = sum((g.dst_slice(t).stop - g.dst_slice(t).start) for t in range(T) if g.mod_active_host[t])
+        alloc = torch.empty if covered == N else torch.zeros
+        x_new = alloc((N, F), dtype=x.dtype, device=x.device)
+        vec_new = alloc((N, 3, F), dtype=x.dtype, device=x.device)
+        saved, spans = [], []
+        for t in range(T):
+            sl = g.dst_slice(t)
+            n = sl.stop - sl.start
+            if n <= 0 or not g.mod_active_host[t]:
+                continue
+            upd = mods[t].update_layer
+            xcat = torch.empty((n, 2 * F), dtype=x.dtype, device=x.device)
+            vecp = torch.empty((n, 3, F), dtype=x.dtype, device=x.device)
+            ops.node_pre(x[sl], dx2[sl], vec[sl], dvec2[sl], xcat, vecp)
+            hi, lo = _wsplit(upd.vec_proj.weight)
+            v12 = ops.gemm_tf32x3_ex(vecp.view(3 * n, F), hi, lo, None)                       # [3n, 2F]
+            vdot = torch.empty((n, F), dtype=x.dtype, device=x.device)
+            ops.node_mid(v12, vdot, xcat)
+            pre2 = torch.empty((n, F), dtype=x.dtype, device=x.device)
+            hi, lo = _wsplit(upd.xvec_proj[0].weight)
+            h2 = ops.gemm_tf32x3_ex(xcat, hi, lo, upd.xvec_proj[0].bias.detach(), mode=1, out2=pre2)
+            hi, lo = _wsplit(upd.xvec_proj[2].weight)
+            a = ops.gemm_tf32x3_ex(h2, hi, lo, upd.xvec_proj[2].bias.detach())                # [n, 3F]
+            ops.node_post(xcat, a, vdot, vecp, v12, x_new[sl], vec_new[sl])
+            saved += [v12, xcat, vdot, a, pre2]
+            spans.append((t, sl))
+        ctx.spans, ctx.mods, ctx.full = spans, mods, covered == N
+        ctx.shapes = (dx.shape, dvec.shape)
+        ctx.save_for_backward(*saved)
+        return x_new, vec_new
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_xn, g_vecn):
+        saved = ctx.saved_tensors
+        g_xn, g_vecn = g_xn.contiguous(), g_vecn.contiguous()
+        N, F = g_xn.shape
+        alloc = torch.empty if ctx.full else torch.zeros
+        g_x = alloc((N, F), dtype=g_xn.dtype, device=g_xn.device)
+        g_vec = alloc((N, 3, F), dtype=g_xn.dtype, device=g_xn.device)
+        for i, (t, sl) in enumerate(ctx.spans):
+            v12, xcat, vdot, a, pre2 = saved[5 * i:5 * i + 5]
+            n = sl.stop - sl.start
+            upd = ctx.mods[t].update_layer
+            g_a = torch.empty((n, 3 * F), dtype=g_xn.dtype, device=g_xn.device)
+            g_vdot = torch.empty((n, F), dtype=g_xn.dtype, device=g_xn.device)
+            g_v12 = torch.empty((3 * n, 2 * F), dtype=g_xn.dtype, device=g_xn.device)
+            ops.node_post_bwd(g_xn[sl], g_vecn[sl], a, vdot, v12, g_a, g_vdot, g_v12)
+            hi, lo = _wsplit(upd.xvec_proj[2].weight, True)                                   # [F, 3F]
+            g_pre2 = ops.gemm_tf32x3_ex(g_a, hi, lo, None, mode=2, aux=pre2)
+            hi, lo = _wsplit(upd.xvec_proj[0].weight, True)                                   # [2F, F]
+            g_cat = ops.gemm_tf32x3_ex(g_pre2, hi, lo, None)
+            ops.node_mid_bwd(g_vdot, g_cat, v12, xcat[:, F:], g_v12)
+            hi, lo = _wsplit(upd.vec_proj.weight, True)                                       # [F, 2F]
+            g_vecp = ops.gemm_tf32x3_ex(g_v12, hi, lo, None)                                  # [3n, F]
+            ops.node_pre_bwd(g_xn[sl], g_cat, g_vecn[sl], g_vecp, g_x[sl], g_vec[sl])
+        dx_shape, dvec_shape = ctx.shapes
+        return g_x, g_vec, g_x.view(dx_shape), g_vec.view(dvec_shape), None, None
+
+
+def node_update_hv(x, vec, dx, dvec, g: RowGraph, mods):
+    return _NodeUpdateHV.apply(x, vec, dx, dvec, g, mods)
+
+
+# ----------------------------------------------------------------------------------------------------
 # composite (any-order differentiable) formulation
 # ----------------------------------------------------------------------------------------------------
 def edge_geometry_composite(pos: Tensor, cell: Optional[Tensor], g: RowGraph) -> Tensor:

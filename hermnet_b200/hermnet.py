@@ -62,6 +62,7 @@ class _HermNet(nn.Module):
         self.pbc_shift = pbc_shift
         self.edge_path = "auto"       # 'auto' | 'fused' | 'composite'
         self.tensor_core_linear = True   # fused path: node-side nn.Linear layers run on tcgen05 (3xTF32 split)
+        self.fused_node = True           # frozen HVNet parameters: fused node-side kernels with hand-written backward
         self.store_features = False   # write data.x / data.vec back like the reference does (hermnet.py:63-64)
 
         self.embed = nn.Embedding(len(atomic_numbers), hidden_channels)
@@ -163,6 +164,13 @@ class _HermNet(nn.Module):
         # LayerNorm_m(x) = xhat * gamma_m + beta_m shares the normalisation: xhat is computed ONCE per layer and the
         # affine part is folded into the first Linear of every sub-network (W1.diag(gamma), b1 + W1.beta) -- the
         # reference runs a full LayerNorm pass over all N rows per sub-network (rmnet.py:52).
+        if self._fused_node_path(conv, p, g):
+            # frozen HVNet parameters on the fused path: hand-written forward/backward for the whole node side
+            xh = Fn.xproj_hv(x, [m.message_layer for m in mods], mods[0].message_layer.x_layernorm.eps)
+            Wt = torch.stack([m.message_layer.rbf_proj.weight.t() for m in mods])
+            bias = torch.stack([m.message_layer.rbf_proj.bias for m in mods])
+            dx, dvec = Fn.painn_edge(xh, vec, geom, Wt, bias, self.radial_basis.rbf.offset, g, p)
+            return Fn.node_update_hv(x, vec, dx, dvec, g, mods)
         xhat = torch.nn.functional.layer_norm(x, (F,), None, None, mods[0].message_layer.x_layernorm.eps)
         w1s, b1s = [], []
         for mod in mods:
@@ -237,6 +245,13 @@ class _HermNet(nn.Module):
         if n_unknown:
             pad(n_unknown)
         return torch.cat(xs, 0), torch.cat(vs, 0)
+
+    def _fused_node_path(self, conv, p, g: RowGraph) -> bool:
+        if p is None or not (self.fused_node and self.tensor_core_linear) or self.KIND != "HVNet":
+            return False
+        if not Fn.node_fusable(self.hidden_channels) or g.rows_per_atom != 1 or g.n_atoms == 0:
+            return False
+        return not any(q.requires_grad for q in conv.parameters())
 
     def _dst_modules(self, t: int):
         """(module id, row slots) of the sub-networks whose destination element is ``t``."""

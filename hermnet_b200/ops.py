@@ -414,3 +414,94 @@ def gemm_tf32x3(a: Tensor, w_hi: Tensor, w_lo: Tensor, bias: Optional[Tensor]) -
         _lib.check(lib.hn_gemm_tf32x3(_ptr(a), M, K, a.stride(0), _ptr(w_hi), _ptr(w_lo), N, _ptr(bias), _ptr(out), N,
                                       _stream(dev)), "hn_gemm_tf32x3")
     return out
+
+
+def _rowmajor(name: str, t: Tensor):
+    """A 2-D float32 CUDA view whose rows are contiguous (row pitch may exceed the row length)."""
+    if t.dim() != 2 or t.stride(1) != 1 or t.stride(0) % 4 != 0 or t.data_ptr() % 16 != 0:
+        raise RuntimeError(f"hermnet_b200.{name}: expected a 16-byte aligned 2-D view with contiguous rows")
+    require_cuda(t, name)
+    _f32(name, t)
+    return t
+
+
+def gemm_tf32x3_ex(a: Tensor, w_hi: Tensor, w_lo: Tensor, bias: Optional[Tensor], out: Optional[Tensor] = None, mode: int = 0,
+                   aux: Optional[Tensor] = None, out2: Optional[Tensor] = None) -> Tensor:
+    """``epilogue(a @ (w_hi + w_lo)^T + bias)`` written into ``out`` (a row-major view, e.g. a column block of a wider
+    buffer); ``mode`` 0 identity / 1 ScaledSiLU with the pre-activation stored in ``out2`` / 2 multiply by
+    ScaledSiLU'(``aux``).  All operands may be row-pitched views."""
+    lib = _lib.load()
+    dev = _chk("gemm_tf32x3_ex", w_hi, w_lo, bias)
+    a = _rowmajor("gemm_tf32x3_ex", a)
+    M, K = a.shape
+    N = w_hi.size(0)
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=dev)
+    _rowmajor("gemm_tf32x3_ex", out)
+    if aux is not None:
+        _rowmajor("gemm_tf32x3_ex", aux)
+    if out2 is not None:
+        _rowmajor("gemm_tf32x3_ex", out2)
+    with torch.cuda.device(dev), _timed("gemm_tf32x3", dev):
+        _lib.check(lib.hn_gemm_tf32x3_ex(_ptr(a), M, K, a.stride(0), _ptr(w_hi), _ptr(w_lo), N, _ptr(bias), _ptr(out), out.stride(0),
+                                         int(mode), _ptr(aux), 4 if aux is None else aux.stride(0), _ptr(out2),
+                                         4 if out2 is None else out2.stride(0), _stream(dev)), "hn_gemm_tf32x3_ex")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------
+# fused element-wise stages of the node update (csrc/hn_node.cu); every tensor is a contiguous row range
+# ----------------------------------------------------------------------------------------------------
+def node_pre(x, dx, vec, dvec, xcat, vecp):
+    """``dx [n,F]`` / ``dvec [n,3,F]`` may be row-pitched views (slot of ``[N,R,F]`` / ``[N,R,3,F]``)."""
+    lib = _lib.load()
+    dev = _chk("node_pre", x, vec, xcat, vecp)
+    n, F = x.shape
+    with torch.cuda.device(dev), _timed("node_elementwise", dev):
+        _lib.check(lib.hn_node_pre(n, F, _ptr(x), _ptr(dx), dx.stride(0), _ptr(vec), _ptr(dvec), dvec.stride(0), _ptr(xcat),
+                                   _ptr(vecp), _stream(dev)), "hn_node_pre")
+
+
+def node_mid(v12, vdot, xcat):
+    lib = _lib.load()
+    dev = _chk("node_mid", v12, vdot, xcat)
+    n, F = vdot.shape
+    with torch.cuda.device(dev), _timed("node_elementwise", dev):
+        _lib.check(lib.hn_node_mid(n, F, _ptr(v12), _ptr(vdot), _ptr(xcat), _stream(dev)), "hn_node_mid")
+
+
+def node_post(xcat, a, vdot, vecp, v12, x_out, vec_out):
+    lib = _lib.load()
+    dev = _chk("node_post", xcat, a, vdot, vecp, v12, x_out, vec_out)
+    n, F = vdot.shape
+    with torch.cuda.device(dev), _timed("node_elementwise", dev):
+        _lib.check(lib.hn_node_post(n, F, _ptr(xcat), _ptr(a), _ptr(vdot), _ptr(vecp), _ptr(v12), _ptr(x_out), _ptr(vec_out),
+                                    _stream(dev)), "hn_node_post")
+
+
+def node_post_bwd(g_x, g_vec, a, vdot, v12, g_a, g_vdot, g_v12):
+    lib = _lib.load()
+    dev = _chk("node_post_bwd", g_x, g_vec, a, vdot, v12, g_a, g_vdot, g_v12)
+    n, F = vdot.shape
+    with torch.cuda.device(dev), _timed("node_elementwise", dev):
+        _lib.check(lib.hn_node_post_bwd(n, F, _ptr(g_x), _ptr(g_vec), _ptr(a), _ptr(vdot), _ptr(v12), _ptr(g_a), _ptr(g_vdot),
+                                        _ptr(g_v12), _stream(dev)), "hn_node_post_bwd")
+
+
+def node_mid_bwd(g_vdot, g_cat, v12, vn, g_v12):
+    """``vn`` may be the second half of the saved ``xcat`` (row pitch 2F)."""
+    lib = _lib.load()
+    dev = _chk("node_mid_bwd", g_vdot, g_cat, v12, g_v12)
+    n, F = g_vdot.shape
+    with torch.cuda.device(dev), _timed("node_elementwise", dev):
+        _lib.check(lib.hn_node_mid_bwd(n, F, _ptr(g_vdot), _ptr(g_cat), _ptr(v12), _ptr(vn), vn.stride(0), _ptr(g_v12),
+                                       _stream(dev)), "hn_node_mid_bwd")
+
+
+def node_pre_bwd(g_xn, g_cat, g_vecn, g_vecp, g_x, g_vec):
+    lib = _lib.load()
+    dev = _chk("node_pre_bwd", g_xn, g_cat, g_vecn, g_vecp, g_x, g_vec)
+    n, F = g_xn.shape
+    with torch.cuda.device(dev), _timed("node_elementwise", dev):
+        _lib.check(lib.hn_node_pre_bwd(n, F, _ptr(g_xn), _ptr(g_cat), _ptr(g_vecn), _ptr(g_vecp), _ptr(g_x), _ptr(g_vec),
+                                       _stream(dev)), "hn_node_pre_bwd")

@@ -216,6 +216,34 @@ int hn_segment_sum(const float *Y, const int32_t *rowptr, const int32_t *perm, i
  * ------------------------------------------------------------------------------------------- */
 int hn_gemm_tf32x3(const float *A, int64_t M, int64_t K, int64_t lda, const float *W_hi, const float *W_lo,
                    int64_t N, const float *bias, float *C, int64_t ldc, void *stream);
+/* Same GEMM with a fused epilogue (ScaledSiLU of rmnet.py:110-117 and its derivative):
+ *   mode 0: C = A.W^T + bias
+ *   mode 1: pre = A.W^T + bias;  C2 = pre (optional, row pitch ldc2);  C = silu(pre)/0.6
+ *   mode 2: C = (A.W^T) * d[silu(z)/0.6]/dz at z = aux[row][col] (row pitch ld_aux) -- backward through the activation */
+int hn_gemm_tf32x3_ex(const float *A, int64_t M, int64_t K, int64_t lda, const float *W_hi, const float *W_lo,
+                      int64_t N, const float *bias, float *C, int64_t ldc, int32_t mode, const float *aux,
+                      int64_t ld_aux, float *C2, int64_t ldc2, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused element-wise stages of the node update (HermNet/rmnet.py:24-32 residuals of PaiNNModule.forward and
+ * rmnet.py:94-107 PaiNNUpdate.forward) and their hand-written backward; n rows, F channels, fp32:
+ *   pre : xcat[:,0:F] = (x + dx)/sqrt2 (xcat row pitch 2F);  vecp = vec + dvec      (dx / dvec row pitches given)
+ *   mid : v12 = [v1 v2] [n,3,2F]:  vdot = sum_k v1*v2/sqrt(F);  xcat[:,F:2F] = sqrt(sum_k v2^2 + 1e-8)
+ *   post: a = [a1 a2 a3] [n,3F]:   x_out = xcat[:,0:F] + (a1 + a2*vdot)/sqrt2;  vec_out = vecp + a3*v1
+ *   post_bwd: g_a, g_vdot, g_v12[...,0:F] from (g_x, g_vec);   mid_bwd: completes g_v12 from (g_vdot, g_cat[:,F:2F]);
+ *   pre_bwd:  g_x (= g_dx) = (g_xn + g_cat[:,0:F])/sqrt2;  g_vec (= g_dvec) = g_vecn + g_vecp
+ * ------------------------------------------------------------------------------------------- */
+int hn_node_pre(int64_t n, int32_t F, const float *x, const float *dx, int64_t ld_dx, const float *vec,
+                const float *dvec, int64_t ld_dvec, float *xcat, float *vecp, void *stream);
+int hn_node_mid(int64_t n, int32_t F, const float *v12, float *vdot, float *xcat, void *stream);
+int hn_node_post(int64_t n, int32_t F, const float *xcat, const float *a, const float *vdot, const float *vecp,
+                 const float *v12, float *x_out, float *vec_out, void *stream);
+int hn_node_post_bwd(int64_t n, int32_t F, const float *g_x, const float *g_vec, const float *a, const float *vdot,
+                     const float *v12, float *g_a, float *g_vdot, float *g_v12, void *stream);
+int hn_node_mid_bwd(int64_t n, int32_t F, const float *g_vdot, const float *g_cat, const float *v12, const float *vn,
+                    int64_t ld_vn, float *g_v12, void *stream);
+int hn_node_pre_bwd(int64_t n, int32_t F, const float *g_xn, const float *g_cat, const float *g_vecn,
+                    const float *g_vecp, float *g_x, float *g_vec, void *stream);
 
 #ifdef __cplusplus
 }

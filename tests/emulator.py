@@ -347,6 +347,80 @@ def gemm_tf32x3(a, w_hi, w_lo, bias):
     return out if bias is None else out + bias
 
 
+def _ssilu(z):
+    return torch.nn.functional.silu(z) / 0.6
+
+
+def _dssilu(z):
+    sg = torch.sigmoid(z)
+    return sg * (1 + z * (1 - sg)) / 0.6
+
+
+def gemm_tf32x3_ex(a, w_hi, w_lo, bias, out=None, mode=0, aux=None, out2=None):
+    acc = a @ (w_hi + w_lo).t()
+    if bias is not None:
+        acc = acc + bias
+    if mode == 1:
+        if out2 is not None:
+            out2.copy_(acc)
+        acc = _ssilu(acc)
+    elif mode == 2:
+        acc = acc * _dssilu(aux)
+    if out is None:
+        return acc
+    out.copy_(acc)
+    return out
+
+
+# fused element-wise stages of the node update (csrc/hn_node.cu), same in-place output contract
+def node_pre(x, dx, vec, dvec, xcat, vecp):
+    F = x.size(1)
+    xcat[:, :F] = (x + dx) * (1 / math.sqrt(2.0))
+    vecp.copy_(vec + dvec.reshape(vec.shape))
+
+
+def node_mid(v12, vdot, xcat):
+    n, F = vdot.shape
+    v = v12.view(n, 3, 2 * F)
+    v1, v2 = v[:, :, :F], v[:, :, F:]
+    vdot.copy_((v1 * v2).sum(1) / math.sqrt(F))
+    xcat[:, F:] = torch.sqrt((v2 * v2).sum(1) + 1e-8)
+
+
+def node_post(xcat, a, vdot, vecp, v12, x_out, vec_out):
+    n, F = vdot.shape
+    a1, a2, a3 = a[:, :F], a[:, F:2 * F], a[:, 2 * F:]
+    x_out.copy_(xcat[:, :F] + (a1 + a2 * vdot) * (1 / math.sqrt(2.0)))
+    vec_out.copy_(vecp + a3[:, None, :] * v12.view(n, 3, 2 * F)[:, :, :F])
+
+
+def node_post_bwd(g_x, g_vec, a, vdot, v12, g_a, g_vdot, g_v12):
+    n, F = vdot.shape
+    c = 1 / math.sqrt(2.0)
+    v1 = v12.view(n, 3, 2 * F)[:, :, :F]
+    g_a[:, :F] = g_x * c
+    g_a[:, F:2 * F] = g_x * c * vdot
+    g_a[:, 2 * F:] = (g_vec * v1).sum(1)
+    g_vdot.copy_(g_x * c * a[:, F:2 * F])
+    g_v12.view(n, 3, 2 * F)[:, :, :F] = g_vec * a[:, None, 2 * F:]
+
+
+def node_mid_bwd(g_vdot, g_cat, v12, vn, g_v12):
+    n, F = g_vdot.shape
+    v = v12.view(n, 3, 2 * F)
+    v1, v2 = v[:, :, :F], v[:, :, F:]
+    gd = g_vdot / math.sqrt(F)
+    gv = g_v12.view(n, 3, 2 * F)
+    gv[:, :, :F] += gd[:, None, :] * v2
+    gv[:, :, F:] = (g_cat[:, F:] / vn)[:, None, :] * v2 + gd[:, None, :] * v1
+
+
+def node_pre_bwd(g_xn, g_cat, g_vecn, g_vecp, g_x, g_vec):
+    F = g_xn.size(1)
+    g_x.copy_((g_xn + g_cat[:, :F]) * (1 / math.sqrt(2.0)))
+    g_vec.copy_(g_vecn + g_vecp.view(g_vecn.shape))
+
+
 def split_tf32(w):
     w = w.detach().contiguous()
     hi = (w.view(torch.int32) & -8192).view(torch.float32)
@@ -358,7 +432,8 @@ def install(monkeypatch):
     for name in ("radius_graph", "sort_by_key", "expand_rowptr", "triplets", "triplet_dots", "edge_geom_fwd",
                  "edge_geom_bwd", "edge_params", "edge_num_slices", "painn_edge_fwd", "painn_edge_bwd_dst",
                  "painn_edge_bwd_src", "painn_edge_bwd_w", "edge_tiled_supported", "edge_tiled_windows", "painn_edge_fwd_tiled",
-                 "painn_edge_bwd_dst_tiled", "painn_edge_bwd_src_tiled", "gather_rows", "segment_sum", "gemm_tf32x3", "split_tf32"):
+                 "painn_edge_bwd_dst_tiled", "painn_edge_bwd_src_tiled", "gemm_tf32x3_ex", "node_pre", "node_mid", "node_post",
+                 "node_post_bwd", "node_mid_bwd", "node_pre_bwd", "gather_rows", "segment_sum", "gemm_tf32x3", "split_tf32"):
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(ops, "require_cuda", lambda t, what: None)
     monkeypatch.setattr(ops, "compute_device", lambda t: t.device)

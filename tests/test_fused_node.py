@@ -1,0 +1,74 @@
+"""Fused node side of an HVNet layer (functional._XProjHV / _NodeUpdateHV over csrc/hn_node.cu + the GEMM epilogues of
+csrc/hn_gemm.cu) against the plain torch formulation of the same layer -- energies, forces and cell gradients."""
+import numpy as np
+import pytest
+import torch
+
+import hermnet_b200 as H
+from tests import util
+from tests.test_tiled_plan import _system
+
+
+def _run(model, pos, Z, cell, fused_node):
+    model.fused_node = fused_node
+    data = H.Data(pos=pos.clone().requires_grad_(True), atomic_number=Z, cell=cell.clone().requires_grad_(True))
+    e = model(data)
+    gp, gc = torch.autograd.grad(e.sum(), [data.pos, data.cell])
+    return e.detach(), gp, gc
+
+
+def _model(elems, F, K, dev, layers=2):
+    torch.manual_seed(3)
+    m = H.HVNet(elems=elems, rc=5.0, num_layers=layers, hidden_channels=F, num_rbf=K).to(dev).eval()
+    for p in m.parameters():
+        p.requires_grad_(False)
+    return m
+
+
+def _compare(model, pos, Z, cell, tol_e=1e-5, tol_f=1e-4):
+    e1, f1, c1 = _run(model, pos, Z, cell, True)
+    e0, f0, c0 = _run(model, pos, Z, cell, False)
+    assert float((e1 - e0).abs().max()) <= tol_e * max(1.0, float(e0.abs().max()))
+    assert float((f1 - f0).abs().max()) <= tol_f * max(1.0, float(f0.abs().max()))
+    assert float((c1 - c0).abs().max()) <= tol_f * max(1.0, float(c0.abs().max()))
+
+
+@pytest.mark.parametrize("elems,zs,F,K", [(["H", "O"], [1, 8], 64, 32), (["H", "O", "C"], [1, 8, 7], 64, 20)])
+def test_fused_node_path_matches_torch_path_on_cpu_emulation(emu, elems, zs, F, K):
+    """zs may contain an element the model does not know (7) and the model an element that is absent (C)."""
+    pos, Z, cell = _system(4, zs, 13)
+    model = _model(elems, F, K, "cpu")
+    assert model._fused_node_path(model.hermconvs[0], object(), model.build_graph(pos, Z, cell))
+    _compare(model, pos, Z, cell)
+
+
+def test_fused_node_path_is_skipped_when_parameters_need_gradients(emu):
+    pos, Z, cell = _system(3, [1, 8], 13)
+    model = _model(["H", "O"], 64, 32, "cpu")
+    for p in model.parameters():
+        p.requires_grad_(True)
+    assert not model._fused_node_path(model.hermconvs[0], object(), model.build_graph(pos, Z, cell))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("elems,zs,F,K,n_side", [(["Li", "Al", "Si", "O"], [3, 13, 14, 8], 128, 128, 9),
+                                                 (["H", "O", "C"], [1, 8, 7], 64, 20, 7),
+                                                 (["Cr", "Fe"], [24, 26], 256, 64, 6)])
+def test_fused_node_path_matches_torch_path(elems, zs, F, K, n_side):
+    pos, Z, cell = _system(n_side, zs, 17)
+    dev = "cuda:0"
+    model = _model(elems, F, K, dev, layers=3)
+    _compare(model, pos.to(dev), Z.to(dev), cell.to(dev))
+
+
+@pytest.mark.gpu
+def test_fused_node_path_on_the_golden_water_box():
+    case = util.load_case("c1_hvnet")
+    model, _ = util.make_model(case["kind"], case["cfg"], case["seed"], "cuda:0")
+    for p in model.parameters():
+        p.requires_grad_(False)
+    data = util.make_data(case, "cuda:0", with_edges=False)
+    assert model._fused_node_path(model.hermconvs[0], object(), model.build_graph(data.pos.detach(), data.atomic_number, data.cell.detach()))
+    e, f, gc = util.energy_forces(model, data)
+    assert util.rel_err(e.cpu(), case["energy"]) < 1e-5
+    assert float((f.cpu() - case["forces"]).abs().max()) < 1e-4
