@@ -95,29 +95,39 @@ def edge_geometry(pos: Tensor, cell: Optional[Tensor], g: RowGraph) -> Tensor:
 
 
 def _plan_geometry(g: RowGraph, geom: Tensor):
-    """``geom`` re-ordered into the slot order of the two TilePlans, cached on the graph for the tensor object in hand
-    (all layers of one evaluation share it)."""
+    """``geom`` re-ordered into the slot order of the edge plans of the graph, cached on the graph for the tensor object
+    in hand (all layers of one evaluation share it).  Returns a dict with keys 'dst', 'src', 'grp' (present plans)."""
     hit = g._lazy.get("plan_geom")
     if hit is not None and hit[0] is geom and hit[1] == geom._version:
-        return hit[2], hit[3]
+        return hit[2]
     gd = geom.detach()
-    geom_b = ops.gather_rows(gd, g.plan_dst.eid)
-    geom_s = ops.gather_rows(gd, g.plan_src.eid) if g.plan_src is not None else None
-    g._lazy["plan_geom"] = (geom, geom._version, geom_b, geom_s)
-    return geom_b, geom_s
+    out = {}
+    if g.plan_dst is not None:
+        out["dst"] = ops.gather_rows(gd, g.plan_dst.eid)
+    if g.plan_src is not None:
+        out["src"] = ops.gather_rows(gd, g.plan_src.eid)
+    if g.plan_grp is not None:
+        out["grp"] = ops.gather_rows(gd, g.plan_grp.eid)
+    g._lazy["plan_geom"] = (geom, geom._version, out)
+    return out
 
 
 class _PaiNNEdge(Function):
+    """Edge side of one layer.  Kernel families, best first: row groups + polynomial filter table (``coef`` given and the
+    graph has a GroupPlan), tiles (TilePlan, opt-in), row per warp (always available)."""
+
     @staticmethod
-    def forward(ctx, xh, vec, geom, Wt, bias, offset, g: RowGraph, p):
+    def forward(ctx, xh, vec, geom, Wt, bias, offset, g: RowGraph, p, coef=None):
         xh, vec, geom, Wt, bias = xh.contiguous(), vec.contiguous(), geom.contiguous(), Wt.contiguous(), bias.contiguous()
+        ctx.group = coef is not None and g.plan_grp is not None and ops.edge_group_supported(p.hidden, p.num_rbf)
         ctx.tiled = g.plan_dst is not None and ops.edge_tiled_supported(p.hidden, p.num_rbf)
-        if ctx.tiled:
-            geom_b, _ = _plan_geometry(g, geom)
-            dx, dvec = ops.painn_edge_fwd_tiled(p, xh, vec, geom_b, g.plan_dst, Wt, bias, offset)
+        if ctx.group:
+            dx, dvec = ops.painn_edge_fwd_group(p, xh, vec, _plan_geometry(g, geom)["grp"], g.plan_grp, coef, bias, offset)
+        elif ctx.tiled:
+            dx, dvec = ops.painn_edge_fwd_tiled(p, xh, vec, _plan_geometry(g, geom)["dst"], g.plan_dst, Wt, bias, offset)
         else:
             dx, dvec = ops.painn_edge_fwd(p, xh, vec, geom, g, Wt, bias, offset)
-        ctx.g, ctx.p = g, p
+        ctx.g, ctx.p, ctx.coef = g, p, coef
         ctx.save_for_backward(xh, vec, geom, Wt, bias, offset)
         return dx, dvec
 
@@ -129,29 +139,31 @@ class _PaiNNEdge(Function):
         g_dx, g_dvec = g_dx.contiguous(), g_dvec.contiguous()
         need = ctx.needs_input_grad
         grad_xh = grad_vec = grad_geom = grad_W = grad_b = None
-        geom_b = geom_s = None
-        if ctx.tiled:
-            geom_b, geom_s = _plan_geometry(g, geom)
+        pg = _plan_geometry(g, geom) if (ctx.group or ctx.tiled) else {}
         if need[2]:
-            if ctx.tiled:
-                parts = ops.painn_edge_bwd_dst_tiled(p, xh, vec, geom_b, g.plan_dst, Wt, bias, offset, g_dx, g_dvec)
+            if ctx.group:
+                parts = ops.painn_edge_bwd_dst_group(p, xh, vec, pg["grp"], g.plan_grp, ctx.coef, bias, offset, g_dx, g_dvec)
+                grad_geom = ops.gather_rows(parts[0] if parts.size(0) == 1 else parts.sum(0), g.plan_grp.pos_of)
+            elif ctx.tiled:
+                parts = ops.painn_edge_bwd_dst_tiled(p, xh, vec, pg["dst"], g.plan_dst, Wt, bias, offset, g_dx, g_dvec)
                 grad_geom = ops.gather_rows(parts[0] if parts.size(0) == 1 else parts.sum(0), g.plan_dst.pos_of)
             else:
                 parts = ops.painn_edge_bwd_dst(p, xh, vec, geom, g, Wt, bias, offset, g_dx, g_dvec)
                 grad_geom = parts[0] if parts.size(0) == 1 else parts.sum(0)
         if need[0] or need[1]:
             if ctx.tiled and g.plan_src is not None:
-                grad_xh, grad_vec = ops.painn_edge_bwd_src_tiled(p, xh, vec, geom_s, g.plan_src, Wt, bias, offset, g_dx, g_dvec)
+                grad_xh, grad_vec = ops.painn_edge_bwd_src_tiled(p, xh, vec, pg["src"], g.plan_src, Wt, bias, offset, g_dx, g_dvec)
             else:
                 grad_xh, grad_vec = ops.painn_edge_bwd_src(p, xh, vec, geom, g, Wt, bias, offset, g_dx, g_dvec)
         if need[3] or need[4]:
             grad_W, grad_b = ops.painn_edge_bwd_w(p, xh, vec, geom, g, offset, g_dx, g_dvec)
-        return grad_xh, grad_vec, grad_geom, grad_W, grad_b, None, None, None
+        return grad_xh, grad_vec, grad_geom, grad_W, grad_b, None, None, None, None
 
 
-def painn_edge(xh, vec, geom, Wt, bias, offset, g: RowGraph, p):
-    """Fused gather -> filter -> message -> segmented reduction.  Returns ``dx [R,F]``, ``dvec [R,3,F]``."""
-    return _PaiNNEdge.apply(xh, vec, geom, Wt, bias, offset, g, p)
+def painn_edge(xh, vec, geom, Wt, bias, offset, g: RowGraph, p, coef=None):
+    """Fused gather -> filter -> message -> segmented reduction.  Returns ``dx [R,F]``, ``dvec [R,3,F]``.
+    ``coef``: piecewise-polynomial table of the filter (filter_table.py) for the row-group kernels."""
+    return _PaiNNEdge.apply(xh, vec, geom, Wt, bias, offset, g, p, coef)
 
 
 # ----------------------------------------------------------------------------------------------------

@@ -166,6 +166,71 @@ def build_tile_plans(g: "RowGraph", d: Tensor, rc: float, num_rbf: int):
     return dst, src
 
 
+GROUP_ROWS = 8   # rows per group of the row-group edge kernels (csrc/hn_edge_group.cu: kGR)
+
+
+@dataclass
+class GroupPlan:
+    """Edge order of the row-group edge kernels: groups of 8 active rows of one sub-network, the group's edges sorted
+    by grid interval of their distance (a performance hint: the kernels re-derive the interval themselves)."""
+    n_groups: int
+    n_slots: int
+    gptr: Tensor         # int32 [n_groups + 1]
+    meta: Tensor         # int32 [n_slots, 4] = (source atom, local row, xh row, interval)
+    eid: Tensor          # int32 [n_slots] row-edge of every slot
+    pos_of: Tensor       # int32 [E] slot of every row-edge (n_slots: edge of an inactive row)
+    group_rows: Tensor   # int32 [n_groups * 8] (-1 = none)
+    group_mod: Tensor    # int32 [n_groups]
+    covers_all_rows: bool = True
+
+
+def build_group_plan(g: "RowGraph", d: Tensor, rc: float, num_rbf: int) -> Optional[GroupPlan]:
+    if g.n_edges == 0 or int(g.xh_base[-1]) >= 2 ** 31:
+        return None
+    dev = d.device
+    M, E, gr, K = g.n_modules, g.n_edges, GROUP_ROWS, num_rbf
+    rm = g.row_mod.long()
+    er = g.edge_row.long()
+    col = g.col.long()
+    u = d * torch.tensor(1.0 / rc, dtype=torch.float32, device=dev)
+    kc = torch.where(u < 1.0, (u * float(K - 1)).long().clamp_(0, K - 2), torch.full_like(er, K - 1))
+    rows_act = torch.nonzero(rm >= 0).squeeze(1)
+    mods_act = rm[rows_act]
+    o = torch.sort(mods_act, stable=True).indices
+    rows_sorted, mods_sorted = rows_act[o], mods_act[o]
+    cnt_dev = torch.bincount(mods_sorted, minlength=M)
+    cnt = cnt_dev.tolist()
+    per_mod = [(c + gr - 1) // gr for c in cnt]
+    base, acc = [], 0
+    for t in per_mod:
+        base.append(acc)
+        acc += t
+    n_groups = acc
+    if n_groups == 0 or n_groups * K >= 2 ** 31 - 2:
+        return None
+    mod_start = torch.cumsum(cnt_dev, 0) - cnt_dev
+    r_in_mod = torch.arange(rows_sorted.numel(), device=dev) - mod_start[mods_sorted]
+    slot = torch.tensor(base, dtype=torch.long, device=dev)[mods_sorted] * gr + r_in_mod
+    group_rows = torch.full((n_groups * gr,), -1, dtype=torch.int32, device=dev)
+    group_rows[slot] = rows_sorted.to(torch.int32)
+    group_mod = torch.repeat_interleave(torch.arange(M, dtype=torch.int32, device=dev),
+                                        torch.tensor(per_mod, dtype=torch.long, device=dev)).contiguous()
+    slot_of_row = torch.full((g.n_rows,), -1, dtype=torch.long, device=dev)
+    slot_of_row[rows_sorted] = slot
+    es = slot_of_row[er]
+    n_keys = n_groups * K
+    key = torch.where(es >= 0, torch.div(es, gr, rounding_mode="floor") * K + kc, torch.full_like(es, n_keys))
+    rowptr, order = ops.sort_by_key(key.to(torch.int32).contiguous(), n_keys + 1)
+    n_slots = int(rowptr[n_keys].item())
+    eid = order.long()[:n_slots]
+    gptr = rowptr[: n_keys + 1: K].contiguous()
+    meta = torch.stack([col[eid], es[eid] % gr, (g.row_xoff[er] + col)[eid], kc[eid]], 1).to(torch.int32).contiguous()
+    pos_of = torch.full((E,), n_slots, dtype=torch.int32, device=dev)
+    pos_of[eid] = torch.arange(n_slots, dtype=torch.int32, device=dev)
+    return GroupPlan(n_groups, n_slots, gptr, meta, eid.to(torch.int32).contiguous(), pos_of, group_rows, group_mod,
+                     covers_all_rows=bool(rows_act.numel() == g.n_rows))
+
+
 class RowGraph:
     def __init__(self):
         self.kind = "HVNet"
@@ -191,6 +256,7 @@ class RowGraph:
         self.energy_index = None      # int32 [N]: graph id of owned atoms, n_graphs for ghosts
         self.plan_dst: Optional[TilePlan] = None   # bucketed edge orders of the tiled edge kernels (None: row kernels)
         self.plan_src: Optional[TilePlan] = None
+        self.plan_grp: Optional[GroupPlan] = None  # edge order of the row-group (piecewise-polynomial filter) kernels
         self._lazy = {}
 
     # ---- lazily built segment views (only the differentiable / training formulation needs them) ----------
@@ -261,6 +327,7 @@ class GraphBuilder:
         self.num_rbf, self.hidden = num_rbf, hidden     # set: also build the TilePlans of the tiled edge kernels
         # (environment switches: A/B measurements only)
         self.tile_plans = os.environ.get("HERMNET_B200_TILED", "0") != "0"
+        self.group_plans = os.environ.get("HERMNET_B200_GROUP", "0") != "0"
         self.spatial_sort = os.environ.get("HERMNET_B200_SPATIAL", "1") != "0"   # Morton order inside every type slice
         if kind not in ("HVNet", "HPNet", "HTNet"):
             raise ValueError(kind)
@@ -530,4 +597,8 @@ class GraphBuilder:
                 and g.n_edges > 0 and ops.edge_tiled_supported(self.hidden, self.num_rbf)):
             d = ops.edge_geom_fwd(pos_i, cell, g)[:, 3].contiguous()
             g.plan_dst, g.plan_src = build_tile_plans(g, d, self.rc, self.num_rbf)
+        if (self.group_plans and pos_i is not None and self.num_rbf is not None and self.hidden is not None
+                and g.n_edges > 0 and ops.edge_group_supported(self.hidden, self.num_rbf)):
+            d = ops.edge_geom_fwd(pos_i, cell, g)[:, 3].contiguous()
+            g.plan_grp = build_group_plan(g, d, self.rc, self.num_rbf)
         return g

@@ -20,6 +20,7 @@ from typing import Dict, List, Optional, Union
 import torch
 from torch import nn
 
+from . import filter_table
 from . import functional as Fn
 from . import ops
 from .graph import GraphBuilder, RowGraph, pair_list
@@ -169,7 +170,7 @@ class _HermNet(nn.Module):
             xh = Fn.xproj_hv(x, [m.message_layer for m in mods], mods[0].message_layer.x_layernorm.eps)
             Wt = torch.stack([m.message_layer.rbf_proj.weight.t() for m in mods])
             bias = torch.stack([m.message_layer.rbf_proj.bias for m in mods])
-            dx, dvec = Fn.painn_edge(xh, vec, geom, Wt, bias, self.radial_basis.rbf.offset, g, p)
+            dx, dvec = Fn.painn_edge(xh, vec, geom, Wt, bias, self.radial_basis.rbf.offset, g, p, self._filter_table(mods, g))
             return Fn.node_update_hv(x, vec, dx, dvec, g, mods)
         xhat = torch.nn.functional.layer_norm(x, (F,), None, None, mods[0].message_layer.x_layernorm.eps)
         w1s, b1s = [], []
@@ -197,7 +198,7 @@ class _HermNet(nn.Module):
         bias = torch.stack([m.message_layer.rbf_proj.bias for m in mods])       # [M,3F]
         # edge side
         if p is not None:
-            dx, dvec = Fn.painn_edge(xh, vec, geom, Wt, bias, self.radial_basis.rbf.offset, g, p)
+            dx, dvec = Fn.painn_edge(xh, vec, geom, Wt, bias, self.radial_basis.rbf.offset, g, p, self._filter_table(mods, g))
         else:
             dx, dvec = Fn.painn_edge_composite_flat(xh, vec, geom, Wt, bias, self.radial_basis, g)
         # node side, part 2: residual + update on the destination-element slices
@@ -245,6 +246,13 @@ class _HermNet(nn.Module):
         if n_unknown:
             pad(n_unknown)
         return torch.cat(xs, 0), torch.cat(vs, 0)
+
+    def _filter_table(self, mods, g: RowGraph):
+        """Polynomial table of every sub-network's radial filter for the row-group edge kernels (None: no GroupPlan)."""
+        if g.plan_grp is None:
+            return None
+        return filter_table.cached_filter_table([m.message_layer.rbf_proj.weight for m in mods],
+                                                self.radial_basis.rbf.offset, self.radial_basis.rbf.coeff)
 
     def _fused_node_path(self, conv, p, g: RowGraph) -> bool:
         if p is None or not (self.fused_node and self.tensor_core_linear) or self.KIND != "HVNet":

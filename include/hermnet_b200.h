@@ -194,6 +194,28 @@ int hn_painn_edge_bwd_src_tiled(const hn_edge_params *p, const float *xh, const 
                                 const float *g_dvec, float *grad_xh /*zeroed*/, float *grad_vec, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Row-group variants of fwd / bwd_dst with a piecewise-polynomial radial filter -- same arithmetic and
+ * reference lines as hn_painn_edge_fwd / _bwd_dst.  coef [M][K-1][10][3F] tabulates, per grid interval
+ * kc of offset[], the degree-9 polynomial in s = 2 (d/rc - offset[kc]) (K-1) - 1 of
+ * sum_k W[m][k][c] gauss_k (built in fp64 by hermnet_b200/filter_table.py; accuracy 8e-8 of max).
+ * Rows are grouped by 8 (one sub-network per group); slots [gptr[g], gptr[g+1]) of group g are its
+ * edges sorted by interval: meta[slot] = (source atom, local row 0..7, xh row, interval), geom_g[slot] =
+ * (ux,uy,uz,d); group_rows int32 [n_groups][8] (-1 = none), group_mod int32 [n_groups].
+ * fwd writes dx/dvec for the rows listed in group_rows; bwd_dst writes g_geom_g[hidden/64][n_slots][4].
+ * Requires hidden % 64 == 0, 64 <= hidden <= 512 (hn_painn_edge_group_supported).
+ * ------------------------------------------------------------------------------------------- */
+int32_t hn_painn_edge_group_supported(int32_t hidden, int32_t num_rbf);
+int hn_painn_edge_fwd_group(const hn_edge_params *p, const float *xh, const float *vec, const float *geom_g,
+                            const int32_t *gptr, const int32_t *meta, const int32_t *group_rows,
+                            const int32_t *group_mod, int32_t n_groups, const float *coef, const float *bias,
+                            const float *offset, float *dx, float *dvec, void *stream);
+int hn_painn_edge_bwd_dst_group(const hn_edge_params *p, const float *xh, const float *vec, const float *geom_g,
+                                const int32_t *gptr, const int32_t *meta, const int32_t *group_rows,
+                                const int32_t *group_mod, int32_t n_groups, const float *coef, const float *bias,
+                                const float *offset, const float *g_dx, const float *g_dvec, float *g_geom_g,
+                                int64_t n_slots, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Row gather / segmented sum -- mutually adjoint linear primitives used by the differentiable
  * (double-backward, training) formulation.  Replace PyG's index_select gathers (rmnet.py:58) and
  * torch_scatter.scatter's atomicAdd (rmnet.py:71-72, hermnet.py:130) with deterministic kernels.

@@ -332,6 +332,75 @@ def painn_edge_bwd_src_tiled(p, xh, vec, geom_s, plan, Wt, bias, offset, g_dx, g
     return grad_xh, grad_vec
 
 
+# ---- row-group kernels with the piecewise-polynomial filter table: slot-by-slot emulation of csrc/hn_edge_group.cu ----
+def edge_group_supported(hidden, num_rbf):
+    return hidden % 64 == 0 and 64 <= hidden <= 512 and num_rbf >= 2
+
+
+def _poly_phi(p, geom_g, coef, bias, offset, m, deriv=False):
+    """phi (and dphi/dd) per slot the way the group kernels evaluate them (Horner on the table, float32)."""
+    K = p.num_rbf
+    u = geom_g[:, 3] * torch.tensor(p.inv_rc, dtype=torch.float32)
+    live = u < 1
+    kc = (u * float(K - 1)).long().clamp(0, K - 2)
+    s = (2.0 * (K - 1)) * (u - offset[kc]) - 1.0
+    c = coef[m, kc]                                           # [E, 10, 3F]
+    pv = c[:, -1]
+    qv = torch.zeros_like(pv)
+    for n in range(c.size(1) - 2, -1, -1):
+        qv = qv * s[:, None] + pv
+        pv = pv * s[:, None] + c[:, n]
+    pp = p.env_p
+    a, b, cc = -0.5 * (pp + 1) * (pp + 2), float(pp * (pp + 2)), -0.5 * pp * (pp + 1)
+    env = 1 + a * u ** pp + b * u ** (pp + 1) + cc * u ** (pp + 2)
+    lv = live.to(pv.dtype)[:, None]
+    phi = bias[m] + env[:, None] * pv * lv
+    if not deriv:
+        return phi, None
+    denv = a * pp * u ** (pp - 1) + b * (pp + 1) * u ** pp + cc * (pp + 2) * u ** (pp + 1)
+    dphi = (denv[:, None] * pv + env[:, None] * qv * (2.0 * (K - 1))) * p.inv_rc * lv
+    return phi, dphi
+
+
+def _grp_slots(plan):
+    lens = (plan.gptr[1:] - plan.gptr[:-1]).long()
+    group = torch.repeat_interleave(torch.arange(plan.n_groups), lens)
+    assert group.numel() == plan.n_slots
+    meta = plan.meta.long()
+    src, lrow, xrow = meta[:, 0], meta[:, 1], meta[:, 2]
+    row = plan.group_rows.long()[group * 8 + lrow]
+    assert (row >= 0).all()
+    return src, xrow, row, plan.group_mod.long()[group]
+
+
+def painn_edge_fwd_group(p, xh, vec, geom_g, plan, coef, bias, offset):
+    F = p.hidden
+    src, xrow, row, m = _grp_slots(plan)
+    phi, _ = _poly_phi(p, geom_g, coef, bias, offset, m)
+    c1, c2 = 1 / math.sqrt(3.0 * F), 1 / math.sqrt(F)
+    a, b, c = torch.split(xh[xrow] * phi, F, dim=-1)
+    mv = vec[src] * (b * c1)[:, None, :] + (c * c2)[:, None, :] * geom_g[:, :3, None]
+    dx = torch.zeros((p.n_rows, F), dtype=xh.dtype).index_add_(0, row, a)
+    dvec = torch.zeros((p.n_rows, 3, F), dtype=xh.dtype).index_add_(0, row, mv)
+    return dx, dvec
+
+
+def painn_edge_bwd_dst_group(p, xh, vec, geom_g, plan, coef, bias, offset, g_dx, g_dvec):
+    F = p.hidden
+    src, xrow, row, m = _grp_slots(plan)
+    phi, dphi = _poly_phi(p, geom_g, coef, bias, offset, m, deriv=True)
+    P, V = xh[xrow], vec[src]
+    gv, tb, tc, c1, c2 = _t_terms(p, V, geom_g, g_dvec, row, F)
+    Pa, Pb, Pc = torch.split(P, F, dim=-1)
+    da, db, dc = torch.split(dphi, F, dim=-1)
+    gd = (g_dx[row] * Pa * da + tb * Pb * db + tc * Pc * dc).sum(1)
+    cphi = Pc * phi[:, 2 * F:] * c2
+    gu = (gv * cphi[:, None, :]).sum(2)
+    out = torch.zeros((F // 64, plan.n_slots + 1, 4), dtype=xh.dtype)
+    out[0, :plan.n_slots] = torch.cat([gu, gd[:, None]], 1)
+    return out
+
+
 def gather_rows(X, idx):
     return X[idx.long()].contiguous()
 
@@ -432,7 +501,8 @@ def install(monkeypatch):
     for name in ("radius_graph", "sort_by_key", "expand_rowptr", "triplets", "triplet_dots", "edge_geom_fwd",
                  "edge_geom_bwd", "edge_params", "edge_num_slices", "painn_edge_fwd", "painn_edge_bwd_dst",
                  "painn_edge_bwd_src", "painn_edge_bwd_w", "edge_tiled_supported", "edge_tiled_windows", "painn_edge_fwd_tiled",
-                 "painn_edge_bwd_dst_tiled", "painn_edge_bwd_src_tiled", "gemm_tf32x3_ex", "node_pre", "node_mid", "node_post",
+                 "painn_edge_bwd_dst_tiled", "painn_edge_bwd_src_tiled", "edge_group_supported", "painn_edge_fwd_group",
+                 "painn_edge_bwd_dst_group", "gemm_tf32x3_ex", "node_pre", "node_mid", "node_post",
                  "node_post_bwd", "node_mid_bwd", "node_pre_bwd", "gather_rows", "segment_sum", "gemm_tf32x3", "split_tf32"):
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(ops, "require_cuda", lambda t, what: None)

@@ -29,6 +29,7 @@ def _model(kind, elems, F, K, dev, layers=2, seed=7):
     for p in m.parameters():
         p.requires_grad_(False)
     m.builder.tile_plans = True     # opt-in while the row kernels are still as fast (HERMNET_B200_TILED=1)
+    m.builder.group_plans = True    # likewise HERMNET_B200_GROUP=1
     return m
 
 
