@@ -22,7 +22,7 @@
 
 namespace {
 
-constexpr int BM = 128, BK = 32, STAGES = 3;
+constexpr int BM = 128, BK = 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -79,30 +79,43 @@ __device__ __forceinline__ float dssilu(float z) {
 
 template <int BN>
 struct Smem {
+    static constexpr int kStages = BN == 128 ? 2 : 3;
     static constexpr int kA = BM * BK * 4;   // 16 KB
     static constexpr int kB = BN * BK * 4;
     static constexpr int kStage = 2 * kA + 2 * kB;
-    static constexpr int kBars = STAGES * kStage;
+    static constexpr int kStaging = kStages * kStage;          // 4 x 16 KB: (C, C2) x double buffer
+    static constexpr int kBars = kStaging + 4 * 16384;
     static constexpr int kTotal = kBars + 256 + 1024;   // barriers + tmem slot, + slack for 1024-byte alignment
 };
 
+// Persistent CTA (one per SM), 384 threads, tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (n-tile fastest):
+//   warp 0    : TMA producer (A raw, W_hi, W_lo K-chunks of 32 floats = one 128-byte swizzle row) into a stage ring
+//   warp 1    : MMA issuer (one thread); accumulators double-buffered in TMEM (2 x BN columns)
+//   warp 2    : TMEM allocation
+//   warps 4-7 : split A in place (hi) + side buffer (lo)
+//   warps 8-11: epilogue of the PREVIOUS tile while the next one is loaded and multiplied:
+//               tcgen05.ld -> +bias / activation -> swizzled staging tile in smem -> TMA store
 template <int BN>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
-                   const __grid_constant__ CUtensorMap tmBlo, const float *__restrict__ bias, float *__restrict__ C,
+                   const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmC,
+                   const __grid_constant__ CUtensorMap tmC2, const float *__restrict__ bias, float *__restrict__ C,
                    int M, int N, int K, long long ldc, int mode, const float *__restrict__ aux, long long ld_aux,
                    float *__restrict__ C2, long long ldc2) {
     extern __shared__ uint8_t smem_raw[];
     using L = Smem<BN>;
+    constexpr int STAGES = L::kStages;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t bars = base + L::kBars;
-    const uint32_t full0 = bars, split0 = bars + 8 * STAGES, empty0 = bars + 16 * STAGES, tfull = bars + 24 * STAGES;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gen + L::kBars + 24 * STAGES + 8);
+    const uint32_t full0 = bars, split0 = bars + 8 * STAGES, empty0 = bars + 16 * STAGES, tfull0 = bars + 24 * STAGES,
+                   tempty0 = tfull0 + 16;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(gen + L::kBars + 24 * STAGES + 40);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
     const int num_k = K / BK;
+    const int n_tiles_n = N / BN;
+    const long long n_tiles = (long long)n_tiles_n * ((M + BM - 1) / BM);
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -110,11 +123,14 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             mbar_init(split0 + 8 * s, 128);
             mbar_init(empty0 + 8 * s, 1);
         }
-        mbar_init(tfull, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull0 + 8 * a, 1);
+            mbar_init(tempty0 + 8 * a, 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        constexpr uint32_t cols = BN < 32 ? 32 : BN;   // power of two >= 32
+        constexpr uint32_t cols = 2 * BN;   // power of two >= 32 (BN in {64, 128})
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -125,83 +141,116 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int kb = 0; kb < num_k; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (kb / STAGES) & 1;
-                mbar_wait(empty0 + 8 * s, ph ^ 1);
-                const uint32_t st = base + s * L::kStage;
-                mbar_expect_tx(full0 + 8 * s, L::kA + 2 * L::kB);
-                tma_load_2d(st, &tmA, full0 + 8 * s, kb * BK, m0);
-                tma_load_2d(st + 2 * L::kA, &tmBhi, full0 + 8 * s, kb * BK, n0);
-                tma_load_2d(st + 2 * L::kA + L::kB, &tmBlo, full0 + 8 * s, kb * BK, n0);
+            long long kbg = 0;                                  // running K-chunk counter (stage ring position)
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int n0 = (int)(tile % n_tiles_n) * BN, m0 = (int)(tile / n_tiles_n) * BM;
+                for (int kb = 0; kb < num_k; ++kb, ++kbg) {
+                    const int s = (int)(kbg % STAGES);
+                    const uint32_t ph = (uint32_t)(kbg / STAGES) & 1;
+                    mbar_wait(empty0 + 8 * s, ph ^ 1);
+                    const uint32_t st = base + s * L::kStage;
+                    mbar_expect_tx(full0 + 8 * s, L::kA + 2 * L::kB);
+                    tma_load_2d(st, &tmA, full0 + 8 * s, kb * BK, m0);
+                    tma_load_2d(st + 2 * L::kA, &tmBhi, full0 + 8 * s, kb * BK, n0);
+                    tma_load_2d(st + 2 * L::kA + L::kB, &tmBlo, full0 + 8 * s, kb * BK, n0);
+                }
             }
         }
     } else if (warp == 1) {
         // instruction descriptor: D=F32 (bit 4), A=B=TF32 (2<<7, 2<<10), K-major A and B, N>>3 at bit 17, M>>4 at bit 24
         const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-        for (int kb = 0; kb < num_k; ++kb) {
-            const int s = kb % STAGES;
-            const uint32_t ph = (kb / STAGES) & 1;
-            mbar_wait(full0 + 8 * s, ph);
-            mbar_wait(split0 + 8 * s, ph);
+        long long kbg = 0, it = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int a = (int)(it & 1);
+            mbar_wait(tempty0 + 8 * a, (uint32_t)((it >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (lane == 0) {
-                const uint32_t st = base + s * L::kStage;
-                const uint32_t a_hi = st, a_lo = st + L::kA, b_hi = st + 2 * L::kA, b_lo = b_hi + L::kB;
+            const uint32_t tacc = tmem_base + (uint32_t)(a * BN);
+            for (int kb = 0; kb < num_k; ++kb, ++kbg) {
+                const int s = (int)(kbg % STAGES);
+                const uint32_t ph = (uint32_t)(kbg / STAGES) & 1;
+                mbar_wait(full0 + 8 * s, ph);
+                mbar_wait(split0 + 8 * s, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) {
+                    const uint32_t st = base + s * L::kStage;
+                    const uint32_t a_hi = st, a_lo = st + L::kA, b_hi = st + 2 * L::kA, b_lo = b_hi + L::kB;
 #pragma unroll
-                for (int k4 = 0; k4 < BK / 8; ++k4) {
-                    const uint32_t off = k4 * 32;   // 8 tf32 = 32 bytes inside the 128-byte swizzle row
-                    umma_tf32(tmem_base, umma_desc(a_hi + off), umma_desc(b_hi + off), idesc, (kb | k4) != 0);
-                    umma_tf32(tmem_base, umma_desc(a_hi + off), umma_desc(b_lo + off), idesc, 1);
-                    umma_tf32(tmem_base, umma_desc(a_lo + off), umma_desc(b_hi + off), idesc, 1);
+                    for (int k4 = 0; k4 < BK / 8; ++k4) {
+                        const uint32_t off = k4 * 32;   // 8 tf32 = 32 bytes inside the 128-byte swizzle row
+                        umma_tf32(tacc, umma_desc(a_hi + off), umma_desc(b_hi + off), idesc, (kb | k4) != 0);
+                        umma_tf32(tacc, umma_desc(a_hi + off), umma_desc(b_lo + off), idesc, 1);
+                        umma_tf32(tacc, umma_desc(a_lo + off), umma_desc(b_hi + off), idesc, 1);
+                    }
+                    umma_commit(empty0 + 8 * s);                          // stage free once these MMAs retire
+                    if (kb == num_k - 1) umma_commit(tfull0 + 8 * a);     // accumulator complete
                 }
-                umma_commit(empty0 + 8 * s);                 // stage free once these MMAs retire
-                if (kb == num_k - 1) umma_commit(tfull);     // accumulator complete
+                __syncwarp();
             }
-            __syncwarp();
         }
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && warp < 8) {
         const int t = threadIdx.x - 128;
-        for (int kb = 0; kb < num_k; ++kb) {
-            const int s = kb % STAGES;
-            const uint32_t ph = (kb / STAGES) & 1;
-            mbar_wait(full0 + 8 * s, ph);
-            float4 *hi = reinterpret_cast<float4 *>(gen + s * L::kStage);
-            float4 *lo = reinterpret_cast<float4 *>(gen + s * L::kStage + L::kA);
+        long long kbg = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            for (int kb = 0; kb < num_k; ++kb, ++kbg) {
+                const int s = (int)(kbg % STAGES);
+                const uint32_t ph = (uint32_t)(kbg / STAGES) & 1;
+                mbar_wait(full0 + 8 * s, ph);
+                float4 *hi = reinterpret_cast<float4 *>(gen + s * L::kStage);
+                float4 *lo = reinterpret_cast<float4 *>(gen + s * L::kStage + L::kA);
 #pragma unroll
-            for (int i = 0; i < L::kA / 16 / 128; ++i) {
-                const float4 v = hi[t + i * 128];
-                float4 h, l;
-                h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-                h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-                h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-                h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-                hi[t + i * 128] = h;
-                lo[t + i * 128] = l;
+                for (int i = 0; i < L::kA / 16 / 128; ++i) {
+                    const float4 v = hi[t + i * 128];
+                    float4 h, l;
+                    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+                    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+                    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+                    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+                    hi[t + i * 128] = h;
+                    lo[t + i * 128] = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
+                mbar_arrive(split0 + 8 * s);
             }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
-            mbar_arrive(split0 + 8 * s);
         }
-        // epilogue: warp w of this group owns TMEM lanes 32*(w%4) .. +31 = output rows m0 + 32*(w%4) + lane
-        mbar_wait(tfull, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    } else if (warp >= 8) {
+        // epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 = output rows m0 + 32*(w%4) + lane.  A 32-column chunk of the
+        // tile is staged in shared memory in the 128-byte-swizzle layout and written with one TMA store -- full 128-byte
+        // lines, rows beyond M clipped -- instead of 16-byte scattered stores, one row per thread.
+        const int t = threadIdx.x - 256;
         const int q = warp & 3;
-        const long long row = (long long)m0 + q * 32 + lane;
+        const int rl = q * 32 + lane;                     // row inside the tile
+        const bool two = (mode == 1 && C2 != nullptr);
+        uint8_t *stg = gen + L::kStaging;
+        int buf = 0;
+        long long it = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int n0 = (int)(tile % n_tiles_n) * BN, m0 = (int)(tile / n_tiles_n) * BM;
+            const long long row = (long long)m0 + rl;
+            const int a = (int)(it & 1);
+            mbar_wait(tfull0 + 8 * a, (uint32_t)((it >> 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t r[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-                  "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-                  "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-                  "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (row < M) {
-                float *dst = C + row * ldc + n0 + c0;
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + c0);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                      "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                      "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                      "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (c0 + 32 >= BN) {       // accumulator fully read: hand it back to the MMA warp
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    asm volatile("bar.sync 2, 128;" ::: "memory");
+                    if (t == 0) mbar_arrive(tempty0 + 8 * a);
+                }
+                uint8_t *sC = stg + buf * 16384, *sC2 = stg + (2 + buf) * 16384;
+                // the TMA store that last read this buffer (two chunks ago) must have finished reading it
+                if (t == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(1) : "memory");
+                asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
                     float4 o = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
@@ -210,22 +259,39 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         const float4 b = __ldg(reinterpret_cast<const float4 *>(bias + n0 + c0 + j));
                         o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
                     }
+                    const int sw = rl * 128 + ((((j >> 2) ^ (rl & 7))) << 4);      // 128-byte swizzle: chunk ^= row % 8
                     if (mode == 1) {          // C2 = pre-activation (optional), C = ScaledSiLU(pre)   (rmnet.py:110-117)
-                        if (C2 != nullptr) *reinterpret_cast<float4 *>(C2 + row * ldc2 + n0 + c0 + j) = o;
+                        if (two) *reinterpret_cast<float4 *>(sC2 + sw) = o;
                         o.x = ssilu(o.x); o.y = ssilu(o.y); o.z = ssilu(o.z); o.w = ssilu(o.w);
                     } else if (mode == 2) {   // C = acc * ScaledSiLU'(aux): backward through the activation
-                        const float4 z = __ldg(reinterpret_cast<const float4 *>(aux + row * ld_aux + n0 + c0 + j));
-                        o.x *= dssilu(z.x); o.y *= dssilu(z.y); o.z *= dssilu(z.z); o.w *= dssilu(z.w);
+                        if (row < M) {
+                            const float4 z = __ldg(reinterpret_cast<const float4 *>(aux + row * ld_aux + n0 + c0 + j));
+                            o.x *= dssilu(z.x); o.y *= dssilu(z.y); o.z *= dssilu(z.z); o.w *= dssilu(z.w);
+                        }
                     }
-                    *reinterpret_cast<float4 *>(dst + j) = o;
+                    *reinterpret_cast<float4 *>(sC + sw) = o;
                 }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> TMA reads
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (t == 0) {
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmC),
+                                 "r"(smem_u32(sC)), "r"(n0 + c0), "r"(m0)
+                                 : "memory");
+                    if (two)
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmC2),
+                                     "r"(smem_u32(sC2)), "r"(n0 + c0), "r"(m0)
+                                     : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                buf ^= 1;
             }
         }
+        if (t == 0) asm volatile("cp.async.bulk.wait_group %0;" ::"n"(0) : "memory");   // writes complete before exit
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 2) {
-        constexpr uint32_t cols = BN < 32 ? 32 : BN;
+        constexpr uint32_t cols = 2 * BN;
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(cols));
     }
 }
@@ -268,13 +334,19 @@ int launch(const float *A, int64_t M, int64_t K, int64_t lda, const float *Whi, 
     HN_REQUIRE(make_map(&ta, A, M, K, lda, BM) == 0, where, "cuTensorMapEncodeTiled failed for A");
     HN_REQUIRE(make_map(&tbh, Whi, N, K, K, BN) == 0, where, "cuTensorMapEncodeTiled failed for W_hi");
     HN_REQUIRE(make_map(&tbl, Wlo, N, K, K, BN) == 0, where, "cuTensorMapEncodeTiled failed for W_lo");
+    CUtensorMap tc, tc2;
+    HN_REQUIRE(make_map(&tc, C, M, N, ldc, BM) == 0, where, "cuTensorMapEncodeTiled failed for C");
+    if (C2 != nullptr) HN_REQUIRE(make_map(&tc2, C2, M, N, ldc2, BM) == 0, where, "cuTensorMapEncodeTiled failed for C2");
+    else tc2 = tc;
     static bool attr_set = false;
     if (!attr_set) {
         HN_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::kTotal), where);
         attr_set = true;
     }
-    dim3 grid((unsigned)(N / BN), (unsigned)((M + BM - 1) / BM));
-    gemm_tf32x3_kernel<BN><<<grid, 256, Smem<BN>::kTotal, st>>>(ta, tbh, tbl, bias, C, (int)M, (int)N, (int)K, (long long)ldc, mode, aux,
+    const long long tiles = (N / BN) * ((M + BM - 1) / BM);
+    const int sms = hn::num_sms() > 0 ? hn::num_sms() : 148;
+    dim3 grid((unsigned)(tiles < sms ? tiles : sms));
+    gemm_tf32x3_kernel<BN><<<grid, 384, Smem<BN>::kTotal, st>>>(ta, tbh, tbl, tc, tc2, bias, C, (int)M, (int)N, (int)K, (long long)ldc, mode, aux,
                                                                  (long long)ld_aux, C2, (long long)ldc2);
     return hn::check_launch(where);
 }

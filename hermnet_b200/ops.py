@@ -74,6 +74,7 @@ def compute_device(t: Tensor) -> torch.device:
 
 # ---- instrumentation used by bench.py: per-kernel CUDA-event timing on the launching stream, launch counting ----
 TIMERS = None          # set to {} to collect name -> [(start_event, end_event), ...]
+GEMM_SHAPES = False    # True: time the tensor-core GEMMs per shape (profiling aid)
 LAUNCHES = {"n": 0}    # hand-written kernels launched through this module (cub passes are not counted)
 
 
@@ -482,7 +483,8 @@ def gemm_tf32x3_ex(a: Tensor, w_hi: Tensor, w_lo: Tensor, bias: Optional[Tensor]
         _rowmajor("gemm_tf32x3_ex", aux)
     if out2 is not None:
         _rowmajor("gemm_tf32x3_ex", out2)
-    with torch.cuda.device(dev), _timed("gemm_tf32x3", dev):
+    tname = f"gemm_tf32x3[{M}x{K}->{N},mode{mode}]" if GEMM_SHAPES else "gemm_tf32x3"
+    with torch.cuda.device(dev), _timed(tname, dev):
         _lib.check(lib.hn_gemm_tf32x3_ex(_ptr(a), M, K, a.stride(0), _ptr(w_hi), _ptr(w_lo), N, _ptr(bias), _ptr(out), out.stride(0),
                                          int(mode), _ptr(aux), 4 if aux is None else aux.stride(0), _ptr(out2),
                                          4 if out2 is None else out2.stride(0), _stream(dev)), "hn_gemm_tf32x3_ex")
