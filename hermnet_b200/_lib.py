@@ -38,6 +38,7 @@ SIGNATURES = {
     "hn_edge_geom_fwd": (c_int32, [P, P, P, P, c_int32, P, P, c_float, c_int64, P, P]),
     "hn_edge_geom_bwd": (c_int32, [P, P, c_int32, P, P, c_int32, P, P, c_float, c_int64, c_int64, P, P, P]),
     "hn_painn_edge_num_slices": (c_int32, [c_int32]),
+    "hn_painn_edge_set_variant": (c_int32, [c_int32]),
     "hn_painn_edge_fwd": (c_int32, [POINTER(EdgeParams)] + [P] * 13),
     "hn_painn_edge_bwd_dst": (c_int32, [POINTER(EdgeParams)] + [P] * 13 + [c_int64, P]),
     "hn_painn_edge_bwd_src": (c_int32, [POINTER(EdgeParams)] + [P] * 16),

@@ -19,7 +19,11 @@
 // Tried and rejected (round 1): 4-edge register tiles sharing each W row over the union of the bands -- fewer
 // L1 bytes but ~1.7x more issued instructions (union window 22 vs 12, shuffle+select per (edge,k)); measured
 // 60/66/138 ms vs 35/42/81 ms per launch at 1M atoms.
+#include <cstdlib>
+#include <cstring>
+
 #include "hn_common.cuh"
+#include "hn_edge_quad.cuh"
 
 namespace {
 
@@ -420,11 +424,36 @@ int validate(const char *where, const hn_edge_params *p) {
     return 0;
 }
 
-}  // namespace
+// HERMNET_B200_EDGE=row forces the row-per-warp kernels of this file (A/B measurements, debugging); the default routes
+// F % 64 == 0 through the quad-tile kernels of hn_edge_quad.cu.
+int g_variant = -1;   // -1: not initialised, 0: auto (quad where supported), 1: row kernels only
 
-extern "C" int32_t hn_painn_edge_num_slices(int32_t hidden) {
+bool use_quad(const hn_edge_params *p) {
+    if (g_variant < 0) {
+        const char *e = getenv("HERMNET_B200_EDGE");
+        g_variant = (e != nullptr && strcmp(e, "row") == 0) ? 1 : 0;
+    }
+    return g_variant == 0 && hn::quad::supported(p);
+}
+
+int row_slices(int hidden) {
     const int v = pick_vec(hidden);
     return v == 0 ? 0 : hidden / (32 * v);
+}
+
+}  // namespace
+
+extern "C" int hn_painn_edge_set_variant(int32_t variant) {
+    HN_REQUIRE(variant == 0 || variant == 1, "hn_painn_edge_set_variant", "variant must be 0 (auto) or 1 (row kernels)");
+    g_variant = variant;
+    return 0;
+}
+
+extern "C" int32_t hn_painn_edge_num_slices(int32_t hidden) {
+    hn_edge_params q = {};
+    q.hidden = hidden;
+    if (row_slices(hidden) != 0 && use_quad(&q)) return hn::quad::bwd_dst_slices(hidden);
+    return row_slices(hidden);
 }
 
 #define HN_DISPATCH_VEC(F, CALL)            \
@@ -441,8 +470,12 @@ extern "C" int hn_painn_edge_fwd(const hn_edge_params *p, const float *xh, const
     const char *where = "hn_painn_edge_fwd";
     if (int rc = validate(where, p)) return rc;
     if (p->n_rows <= 0) return 0;
+    if (use_quad(p)) {
+        hn::quad::fwd(p, xh, vec, geom, rowptr, col, row_mod, row_xoff, Wt, bias, offset, dx, dvec, (cudaStream_t)stream);
+        return hn::check_launch(where);
+    }
     const int wpb = 8;
-    dim3 grid((p->n_rows + wpb - 1) / wpb, hn_painn_edge_num_slices(p->hidden));
+    dim3 grid((p->n_rows + wpb - 1) / wpb, row_slices(p->hidden));
     HN_DISPATCH_VEC(p->hidden, (edge_fwd_kernel<VEC><<<grid, 32 * wpb, 0, (cudaStream_t)stream>>>(
                                    *p, xh, vec, (const float4 *)geom, rowptr, col, row_mod, (const long long *)row_xoff, Wt, bias, offset, dx,
                                    dvec)));
@@ -456,8 +489,13 @@ extern "C" int hn_painn_edge_bwd_dst(const hn_edge_params *p, const float *xh, c
     const char *where = "hn_painn_edge_bwd_dst";
     if (int rc = validate(where, p)) return rc;
     if (p->n_rows <= 0 || n_edges <= 0) return 0;
+    if (use_quad(p)) {
+        hn::quad::bwd_dst(p, xh, vec, geom, rowptr, col, row_mod, row_xoff, Wt, bias, offset, g_dx, g_dvec, g_geom, n_edges,
+                          (cudaStream_t)stream);
+        return hn::check_launch(where);
+    }
     const int wpb = 8;
-    dim3 grid((p->n_rows + wpb - 1) / wpb, hn_painn_edge_num_slices(p->hidden));
+    dim3 grid((p->n_rows + wpb - 1) / wpb, row_slices(p->hidden));
     HN_DISPATCH_VEC(p->hidden, (edge_bwd_dst_kernel<VEC><<<grid, 32 * wpb, 0, (cudaStream_t)stream>>>(
                                    *p, xh, vec, (const float4 *)geom, rowptr, col, row_mod, (const long long *)row_xoff, Wt, bias, offset,
                                    g_dx, g_dvec, (float4 *)g_geom, n_edges)));
@@ -473,7 +511,7 @@ extern "C" int hn_painn_edge_bwd_src(const hn_edge_params *p, const float *xh, c
     if (int rc = validate(where, p)) return rc;
     if (p->n_atoms <= 0) return 0;
     const int wpb = 8;
-    dim3 grid((p->n_atoms + wpb - 1) / wpb, hn_painn_edge_num_slices(p->hidden));
+    dim3 grid((p->n_atoms + wpb - 1) / wpb, row_slices(p->hidden));
     HN_DISPATCH_VEC(p->hidden, (edge_bwd_src_kernel<VEC><<<grid, 32 * wpb, 0, (cudaStream_t)stream>>>(
                                    *p, xh, vec, (const float4 *)geom, t_rowptr, t_eid, edge_row, row_mod, (const long long *)row_xoff, Wt,
                                    bias, offset, g_dx, g_dvec, grad_xh, grad_vec)));

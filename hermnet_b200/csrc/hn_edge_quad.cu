@@ -1,0 +1,514 @@
+// Tile-sweep PaiNN edge kernels: forward and destination-major backward (default for F in {64, 128, 256, 512}).
+//
+// Same arithmetic and reference lines as hn_edge.cu (rmnet.py:55-73 message/aggregate, rmnet.py:168-193 Gaussian RBF x
+// polynomial envelope, hermnet.py:51-61 per-element sub-networks):
+//   phi_e = W[m] . (env(u) * gauss_k(u)) + b[m],  u = d_e / rc
+//   dx[r] = sum_e xh[m][s][0:F] * phi_e[0:F],   dvec[r][k] = sum_e (vec[s][k]*xh_b*phi_b/sqrt(3) + xh_c*phi_c*u_e[k]) / sqrt(F)
+//
+// Why another loop nest.  The row-per-warp kernels re-read a 12 x 3F band of W for EVERY edge: 18 KB of L1 traffic
+// per edge at F=128 against 3 KB of gathered features, and ncu shows them pinned at >80 % of the L1/LSU peak.  Rows
+// are sorted by distance by the graph builder, so CONSECUTIVE edges of a row have overlapping bands.  Here a warp
+// walks its row in tiles of T consecutive edges (forward T=4, backward T=2) and sweeps the UNION of the tile's bands
+// once: every W row it loads feeds T edges of packed FMAs (fma.rn.f32x2).
+//   * per tile, lane (q = lane % T, sub = lane / T) evaluates env*gauss_k(d_q) for k = kmin+sub, +32/T, ... of the
+//     union (exact Gaussian values, also outside the edge's own 12-wide band -- those terms are < 1.5e-8 and were
+//     dropped by the row kernels) into a per-warp shared-memory table of (g,g) pairs; the sweep broadcasts them with
+//     LDS.128 and needs no shuffles;
+//   * the union is a 64-bit mask relative to kmin (holes between distance shells are skipped); when the bands of a
+//     tile span more than 64 basis functions (rows that are no longer distance-sorted because the graph is re-used
+//     after the atoms moved) the tile falls back to a single edge: sharing is lost, accuracy never;
+//   * accumulation per row stays private to the warp: no atomics, deterministic order;
+//   * F is a template parameter, so every address inside the sweep is base + immediate.
+#include "hn_common.cuh"
+#include "hn_edge_quad.cuh"
+
+namespace {
+
+typedef unsigned long long u64;
+
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kTabW = 64;         // basis functions a tile's union may span
+constexpr int kLo = 5, kHi = 6;   // band = floor(x)-5 .. floor(x)+6, x = u*(K-1)  (same band as hn_edge.cu)
+constexpr int kWarps = 8;
+constexpr int kBig = 1 << 20;
+
+__device__ __forceinline__ u64 pk(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk(u64 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
+    u64 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// NP packed pairs (= 2*NP consecutive channels) from global memory through the read-only path
+template <int NP>
+struct Pairs {
+    u64 p[NP];
+};
+template <int NP>
+__device__ __forceinline__ Pairs<NP> ldp(const float *ptr) {
+    Pairs<NP> r;
+    if constexpr (NP == 2) {
+        const ulonglong2 t = __ldg(reinterpret_cast<const ulonglong2 *>(ptr));
+        r.p[0] = t.x;
+        r.p[1] = t.y;
+    } else {
+        r.p[0] = __ldg(reinterpret_cast<const u64 *>(ptr));
+    }
+    return r;
+}
+
+// polynomial envelope (rmnet.py:183-193) and its derivative with respect to u
+template <bool DERIV>
+__device__ __forceinline__ void envelope(float u, int p, float &env, float &denv) {
+    const float a = -0.5f * (float)((p + 1) * (p + 2)), b = (float)(p * (p + 2)), c = -0.5f * (float)(p * (p + 1));
+    float um;
+    if (p == 5) {
+        const float u2 = u * u;
+        um = u2 * u2;
+    } else {
+        um = 1.f;
+        for (int i = 0; i < p - 1; ++i) um *= u;
+    }
+    const float u0 = um * u, u1 = u0 * u, u2 = u1 * u;
+    env = 1.f + a * u0 + b * u1 + c * u2;
+    denv = 0.f;
+    if (DERIV) denv = a * (float)p * um + b * (float)(p + 1) * u0 + c * (float)(p + 2) * u1;
+}
+
+// Edge eb + (lane % T) of the row: source atom and geometry (zeros past the end of the row).
+template <int T>
+struct Head {
+    float4 g;
+    int s;
+};
+template <int T>
+__device__ __forceinline__ Head<T> load_head(const float4 *__restrict__ geom, const int *__restrict__ col, int eb, int e1,
+                                             int lane) {
+    Head<T> h;
+    const int e = eb + (lane & (T - 1));
+    h.g = make_float4(0.f, 0.f, 0.f, 0.f);
+    h.s = -1;
+    if (e < e1) {
+        h.g = __ldg(geom + e);
+        h.s = __ldg(col + e);
+    }
+    return h;
+}
+
+// Sets up the tile whose head (edges eb .. eb+T-1, h.s < 0 past the row end) was loaded by load_head.  Returns the
+// number of edges the tile takes (T, fewer at the end of a row, 1 when the bands span >= kTabW basis functions) and
+// fills tab[kk][2q..2q+1] = env*gauss_{kmin+kk}(d_q) (DERIV: tab[kTabW + kk] = d/dd of it) for every kk of the mask.
+template <int T, bool DERIV>
+__device__ __forceinline__ int tile_setup(const hn_edge_params &P, const float *__restrict__ offset, const Head<T> &h,
+                                          int n_left, int lane, float *tab, int &kmin, u64 &mask) {
+    constexpr int NSUB = 32 / T;
+    const int q = lane & (T - 1), sub = lane / T;
+    const int K = P.num_rbf;
+    const float u = h.g.w * P.inv_rc;
+    const bool valid = h.s >= 0 && u < 1.f;
+    int lo = kBig, hi = -1;
+    if (valid) {
+        const int kc = (int)(u * (float)(K - 1));
+        lo = max(kc - kLo, 0);
+        hi = min(kc + kHi, K - 1);
+    }
+    int mn = lo, mx = hi;
+#pragma unroll
+    for (int o = 1; o < T; o <<= 1) {
+        mn = min(mn, __shfl_xor_sync(kFull, mn, o));
+        mx = max(mx, __shfl_xor_sync(kFull, mx, o));
+    }
+    int cnt = n_left < T ? n_left : T;
+    if (mx - mn >= kTabW) {        // not distance-sorted: take the first edge alone
+        cnt = 1;
+        mn = __shfl_sync(kFull, lo, 0);
+        mx = __shfl_sync(kFull, hi, 0);
+    }
+    const bool act = valid && q < cnt;
+    u64 bits = 0ull;
+    if (act) bits = ((2ull << (hi - lo)) - 1ull) << (lo - mn);
+    const unsigned b_lo = __reduce_or_sync(kFull, (unsigned)bits), b_hi = __reduce_or_sync(kFull, (unsigned)(bits >> 32));
+    mask = ((u64)b_hi << 32) | (u64)b_lo;
+    kmin = mn;
+    const int width = mx - mn + 1;    // <= kTabW; <= 0 when no edge of the tile is inside the cutoff
+    float env = 0.f, denv = 0.f;
+    if (act) envelope<DERIV>(u, P.env_p, env, denv);
+    const float *off = offset + mn;
+    for (int kk = sub; kk < width; kk += NSUB) {
+        if ((mask >> kk) & 1ull) {
+            float val = 0.f, dval = 0.f;
+            if (act) {
+                const float diff = u - __ldg(off + kk);
+                const float gg = __expf(P.coeff * diff * diff);
+                val = env * gg;
+                if (DERIV) dval = (denv * gg + val * (2.f * P.coeff * diff)) * P.inv_rc;
+            }
+            *reinterpret_cast<float2 *>(tab + kk * (2 * T) + 2 * q) = make_float2(val, val);
+            if (DERIV) *reinterpret_cast<float2 *>(tab + (kTabW + kk) * (2 * T) + 2 * q) = make_float2(dval, dval);
+        }
+    }
+    __syncwarp();
+    return cnt;
+}
+
+// (g,g) pairs of the T edges of a tile for table row kk
+template <int T>
+__device__ __forceinline__ void load_pairs(const float *tab_row, u64 (&gg)[T]) {
+    if constexpr (T == 4) {
+        const ulonglong2 a = *reinterpret_cast<const ulonglong2 *>(tab_row), b = *reinterpret_cast<const ulonglong2 *>(tab_row + 4);
+        gg[0] = a.x;
+        gg[1] = a.y;
+        gg[2] = b.x;
+        gg[3] = b.y;
+    } else {
+        const ulonglong2 a = *reinterpret_cast<const ulonglong2 *>(tab_row);
+        gg[0] = a.x;
+        gg[1] = a.y;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// forward.  One warp = one (row, slice of 64*NP channels); the slices of a row sit in the same CTA.
+// ---------------------------------------------------------------------------------------------------------------
+template <int F, int NP>
+__global__ void __launch_bounds__(32 * kWarps, 2)
+edge_fwd_quad_kernel(const hn_edge_params P, const float *__restrict__ xh, const float *__restrict__ vec,
+                     const float4 *__restrict__ geom, const int *__restrict__ rowptr, const int *__restrict__ col,
+                     const int *__restrict__ row_mod, const long long *__restrict__ row_xoff, const float *__restrict__ Wt,
+                     const float *__restrict__ bias, const float *__restrict__ offset, float *__restrict__ dx,
+                     float *__restrict__ dvec) {
+    constexpr int T = 4, VEC = 2 * NP, F3 = 3 * F, NS = F / (32 * VEC);
+    __shared__ __align__(16) float s_tab[kWarps][kTabW * 2 * T];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int unit = blockIdx.x * kWarps + warp;
+    const int row = unit / NS, slice = unit % NS;
+    if (row >= P.n_rows) return;
+    const int ch = slice * (32 * VEC) + lane * VEC;
+    const int m = __ldg(row_mod + row);
+    float *tab = s_tab[warp];
+    float ax[VEC], av[3][VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) ax[v] = av[0][v] = av[1][v] = av[2][v] = 0.f;
+    if (m >= 0) {
+        const int e0 = __ldg(rowptr + row), e1 = __ldg(rowptr + row + 1);
+        const float *Wm = Wt + (size_t)m * P.num_rbf * F3 + ch;
+        const float *xm = xh + __ldg(row_xoff + row) * F3 + ch;
+        const float *vm = vec + ch;
+        const float *bm = bias + (size_t)m * F3 + ch;
+        const float c1 = 1.0f / sqrtf(3.0f * (float)F), c2 = 1.0f / sqrtf((float)F);
+        int eb = e0;
+        Head<T> h = load_head<T>(geom, col, eb, e1, lane);
+        while (eb < e1) {
+            int kmin;
+            u64 mask;
+            const int cnt = tile_setup<T, false>(P, offset, h, e1 - eb, lane, tab, kmin, mask);
+            const Head<T> hn = load_head<T>(geom, col, eb + cnt, e1, lane);    // next tile's head, in flight during the sweep
+            u64 fa[T][NP], fb[T][NP], fc[T][NP];
+            {
+                const Pairs<NP> ba = ldp<NP>(bm), bb = ldp<NP>(bm + F), bc = ldp<NP>(bm + 2 * F);
+#pragma unroll
+                for (int j = 0; j < T; ++j)
+#pragma unroll
+                    for (int n = 0; n < NP; ++n) {
+                        fa[j][n] = ba.p[n];
+                        fb[j][n] = bb.p[n];
+                        fc[j][n] = bc.p[n];
+                    }
+            }
+            const float *w = Wm + (size_t)kmin * F3;
+            const float *t = tab;
+            for (u64 mk = mask; mk != 0ull; mk >>= 1, w += F3, t += 2 * T) {
+                if (mk & 1ull) {
+                    const Pairs<NP> wa = ldp<NP>(w), wb = ldp<NP>(w + F), wc = ldp<NP>(w + 2 * F);
+                    u64 gg[T];
+                    load_pairs<T>(t, gg);
+#pragma unroll
+                    for (int j = 0; j < T; ++j)
+#pragma unroll
+                        for (int n = 0; n < NP; ++n) {
+                            fa[j][n] = fma2(gg[j], wa.p[n], fa[j][n]);
+                            fb[j][n] = fma2(gg[j], wb.p[n], fb[j][n]);
+                            fc[j][n] = fma2(gg[j], wc.p[n], fc[j][n]);
+                        }
+                }
+            }
+            __syncwarp();    // table reads done before the next tile's fill
+#pragma unroll
+            for (int j = 0; j < T; ++j) {
+                if (j < cnt) {
+                    const int sj = __shfl_sync(kFull, h.s, j);
+                    const float ux = __shfl_sync(kFull, h.g.x, j), uy = __shfl_sync(kFull, h.g.y, j), uz = __shfl_sync(kFull, h.g.z, j);
+                    const float *xs = xm + (size_t)sj * F3;
+                    const float *vs = vm + (size_t)sj * F3;
+                    const Pairs<NP> Pa = ldp<NP>(xs), Pb = ldp<NP>(xs + F), Pc = ldp<NP>(xs + 2 * F);
+                    const Pairs<NP> V0 = ldp<NP>(vs), V1 = ldp<NP>(vs + F), V2 = ldp<NP>(vs + 2 * F);
+#pragma unroll
+                    for (int n = 0; n < NP; ++n) {
+                        float pa[2], pb[2], pc[2], v0[2], v1[2], v2[2], qa[2], qb[2], qc[2];
+                        upk(Pa.p[n], pa[0], pa[1]);
+                        upk(Pb.p[n], pb[0], pb[1]);
+                        upk(Pc.p[n], pc[0], pc[1]);
+                        upk(V0.p[n], v0[0], v0[1]);
+                        upk(V1.p[n], v1[0], v1[1]);
+                        upk(V2.p[n], v2[0], v2[1]);
+                        upk(fa[j][n], qa[0], qa[1]);
+                        upk(fb[j][n], qb[0], qb[1]);
+                        upk(fc[j][n], qc[0], qc[1]);
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            const int v = 2 * n + hh;
+                            ax[v] = fmaf(pa[hh], qa[hh], ax[v]);
+                            const float tb = pb[hh] * qb[hh] * c1;
+                            const float tc = pc[hh] * qc[hh] * c2;
+                            av[0][v] += v0[hh] * tb + tc * ux;
+                            av[1][v] += v1[hh] * tb + tc * uy;
+                            av[2][v] += v2[hh] * tb + tc * uz;
+                        }
+                    }
+                }
+            }
+            eb += cnt;
+            h = hn;
+        }
+    }
+    hn::Vec<VEC> o;
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) o.v[v] = ax[v];
+    hn::stv<VEC>(dx + (size_t)row * F + ch, o);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) o.v[v] = av[k][v];
+        hn::stv<VEC>(dvec + (size_t)row * F3 + (size_t)k * F + ch, o);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// destination-major backward: per row-edge (dL/du_x, dL/du_y, dL/du_z, dL/dd), one plane per channel slice.
+//   dL/dd  = sum_c [ gx Pa phi_a' + tb Pb phi_b' + tc Pc phi_c' ],  phi' = sum_k W_k d(env g_k)/dd
+//          = sum_k h_k(d) . sum_c (qa W_a[k] + qb W_b[k] + qc W_c[k]),  qa = gx Pa, qb = tb Pb, qc = tc Pc
+//   dL/du  = sum_c gv[.] Pc phi_c / sqrt(F)
+// tb = <gv, V>/sqrt(3F), tc = <gv, u>/sqrt(F) as in hn_edge.cu.  Tiles of 2 edges (the sweep carries 11 packed
+// registers per edge); the gathers are issued before the sweep, so their latency hides behind it.  The 8 per-tile
+// partial sums (2 edges x 4 values) are reduced across the warp with a halving exchange (8 shuffles instead of 40).
+// ---------------------------------------------------------------------------------------------------------------
+template <int F, int NP>
+__global__ void __launch_bounds__(32 * kWarps, 2)
+edge_bwd_dst_quad_kernel(const hn_edge_params P, const float *__restrict__ xh, const float *__restrict__ vec,
+                         const float4 *__restrict__ geom, const int *__restrict__ rowptr, const int *__restrict__ col,
+                         const int *__restrict__ row_mod, const long long *__restrict__ row_xoff, const float *__restrict__ Wt,
+                         const float *__restrict__ bias, const float *__restrict__ offset, const float *__restrict__ g_dx,
+                         const float *__restrict__ g_dvec, float4 *__restrict__ g_geom, long long n_edges) {
+    constexpr int T = 2, VEC = 2 * NP, F3 = 3 * F, NS = F / (32 * VEC);
+    __shared__ __align__(16) float s_tab[kWarps][2 * kTabW * 2 * T];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int unit = blockIdx.x * kWarps + warp;
+    const int row = unit / NS, slice = unit % NS;
+    if (row >= P.n_rows) return;
+    const int ch = slice * (32 * VEC) + lane * VEC;
+    const int m = __ldg(row_mod + row);
+    const int e0 = __ldg(rowptr + row), e1 = __ldg(rowptr + row + 1);
+    float4 *out = g_geom + (size_t)slice * n_edges;
+    if (m < 0) {
+        for (int e = e0 + lane; e < e1; e += 32) out[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+    float *tab = s_tab[warp];
+    const float *Wm = Wt + (size_t)m * P.num_rbf * F3 + ch;
+    const float *xm = xh + __ldg(row_xoff + row) * F3 + ch;
+    const float *vm = vec + ch;
+    const Pairs<NP> bc = ldp<NP>(bias + (size_t)m * F3 + 2 * F + ch);
+    float gx[VEC], gv[3][VEC];
+    {
+        const hn::Vec<VEC> t = hn::ldv<VEC>(g_dx + (size_t)row * F + ch);
+        const hn::Vec<VEC> t0 = hn::ldv<VEC>(g_dvec + (size_t)row * F3 + ch), t1 = hn::ldv<VEC>(g_dvec + (size_t)row * F3 + F + ch),
+                           t2 = hn::ldv<VEC>(g_dvec + (size_t)row * F3 + 2 * F + ch);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            gx[v] = t.v[v];
+            gv[0][v] = t0.v[v];
+            gv[1][v] = t1.v[v];
+            gv[2][v] = t2.v[v];
+        }
+    }
+    const float c1 = 1.0f / sqrtf(3.0f * (float)F), c2 = 1.0f / sqrtf((float)F);
+    int eb = e0;
+    Head<T> h = load_head<T>(geom, col, eb, e1, lane);
+    while (eb < e1) {
+        // gathers of the T edges first (independent of the table), then the table, then the sweep
+        Pairs<NP> Pa[T], Pb[T], Pc[T], V0[T], V1[T], V2[T];
+        float ux[T], uy[T], uz[T];
+#pragma unroll
+        for (int j = 0; j < T; ++j) {
+            int sj = __shfl_sync(kFull, h.s, j);
+            ux[j] = __shfl_sync(kFull, h.g.x, j);
+            uy[j] = __shfl_sync(kFull, h.g.y, j);
+            uz[j] = __shfl_sync(kFull, h.g.z, j);
+            if (sj < 0) sj = __shfl_sync(kFull, h.s, 0);   // past the row end: a valid address, the result is discarded
+            const float *xs = xm + (size_t)sj * F3;
+            const float *vs = vm + (size_t)sj * F3;
+            Pa[j] = ldp<NP>(xs);
+            Pb[j] = ldp<NP>(xs + F);
+            Pc[j] = ldp<NP>(xs + 2 * F);
+            V0[j] = ldp<NP>(vs);
+            V1[j] = ldp<NP>(vs + F);
+            V2[j] = ldp<NP>(vs + 2 * F);
+        }
+        int kmin;
+        u64 mask;
+        const int cnt = tile_setup<T, true>(P, offset, h, e1 - eb, lane, tab, kmin, mask);
+        const Head<T> hn = load_head<T>(geom, col, eb + cnt, e1, lane);
+        u64 qa[T][NP], qb[T][NP], qc[T][NP], fc[T][NP], ds[T];
+        float rc_[T][VEC];    // Pc / sqrt(F): the u-independent factor of dL/du
+#pragma unroll
+        for (int j = 0; j < T; ++j) {
+            ds[j] = 0ull;
+#pragma unroll
+            for (int n = 0; n < NP; ++n) {
+                fc[j][n] = bc.p[n];
+                float pa[2], pb[2], pc[2], v0[2], v1[2], v2[2], a_[2], b_[2], c_[2];
+                upk(Pa[j].p[n], pa[0], pa[1]);
+                upk(Pb[j].p[n], pb[0], pb[1]);
+                upk(Pc[j].p[n], pc[0], pc[1]);
+                upk(V0[j].p[n], v0[0], v0[1]);
+                upk(V1[j].p[n], v1[0], v1[1]);
+                upk(V2[j].p[n], v2[0], v2[1]);
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int v = 2 * n + hh;
+                    const float tb = (gv[0][v] * v0[hh] + gv[1][v] * v1[hh] + gv[2][v] * v2[hh]) * c1;
+                    const float tc = (gv[0][v] * ux[j] + gv[1][v] * uy[j] + gv[2][v] * uz[j]) * c2;
+                    a_[hh] = gx[v] * pa[hh];
+                    b_[hh] = tb * pb[hh];
+                    c_[hh] = tc * pc[hh];
+                    rc_[j][v] = pc[hh] * c2;
+                }
+                qa[j][n] = pk(a_[0], a_[1]);
+                qb[j][n] = pk(b_[0], b_[1]);
+                qc[j][n] = pk(c_[0], c_[1]);
+            }
+        }
+        const float *w = Wm + (size_t)kmin * F3;
+        const float *t = tab;
+        for (u64 mk = mask; mk != 0ull; mk >>= 1, w += F3, t += 2 * T) {
+            if (mk & 1ull) {
+                const Pairs<NP> wa = ldp<NP>(w), wb = ldp<NP>(w + F), wc = ldp<NP>(w + 2 * F);
+                u64 gg[T], hh[T];
+                load_pairs<T>(t, gg);
+                load_pairs<T>(t + kTabW * 2 * T, hh);
+#pragma unroll
+                for (int j = 0; j < T; ++j) {
+                    u64 tt = mul2(qa[j][0], wa.p[0]);
+                    tt = fma2(qb[j][0], wb.p[0], tt);
+                    tt = fma2(qc[j][0], wc.p[0], tt);
+                    fc[j][0] = fma2(gg[j], wc.p[0], fc[j][0]);
+                    if constexpr (NP == 2) {
+                        tt = fma2(qa[j][1], wa.p[1], tt);
+                        tt = fma2(qb[j][1], wb.p[1], tt);
+                        tt = fma2(qc[j][1], wc.p[1], tt);
+                        fc[j][1] = fma2(gg[j], wc.p[1], fc[j][1]);
+                    }
+                    ds[j] = fma2(hh[j], tt, ds[j]);
+                }
+            }
+        }
+        __syncwarp();
+        // per-lane partial sums: val[4*j + {0,1,2}] = dL/du, val[4*j + 3] = dL/dd
+        float val[4 * T];
+#pragma unroll
+        for (int j = 0; j < T; ++j) {
+            float d0, d1, gu0 = 0.f, gu1 = 0.f, gu2 = 0.f;
+            upk(ds[j], d0, d1);
+#pragma unroll
+            for (int n = 0; n < NP; ++n) {
+                float f_[2];
+                upk(fc[j][n], f_[0], f_[1]);
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int v = 2 * n + hh;
+                    const float cphi = rc_[j][v] * f_[hh];
+                    gu0 = fmaf(gv[0][v], cphi, gu0);
+                    gu1 = fmaf(gv[1][v], cphi, gu1);
+                    gu2 = fmaf(gv[2][v], cphi, gu2);
+                }
+            }
+            val[4 * j + 0] = gu0;
+            val[4 * j + 1] = gu1;
+            val[4 * j + 2] = gu2;
+            val[4 * j + 3] = d0 + d1;
+        }
+        // halving exchange over lane bits 16, 8, 4 (value-index bits 4, 2, 1), then plain butterflies over bits 2, 1
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const bool up = lane & 16;
+            const float send = up ? val[i] : val[i + 4], keep = up ? val[i + 4] : val[i];
+            val[i] = keep + __shfl_xor_sync(kFull, send, 16);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const bool up = lane & 8;
+            const float send = up ? val[i] : val[i + 2], keep = up ? val[i + 2] : val[i];
+            val[i] = keep + __shfl_xor_sync(kFull, send, 8);
+        }
+        {
+            const bool up = lane & 4;
+            const float send = up ? val[0] : val[1], keep = up ? val[1] : val[0];
+            val[0] = keep + __shfl_xor_sync(kFull, send, 4);
+        }
+        val[0] += __shfl_xor_sync(kFull, val[0], 2);
+        val[0] += __shfl_xor_sync(kFull, val[0], 1);
+        // lane holds the total of value index idx = lane >> 2: edge idx >> 2, component idx & 3
+        const int idx = lane >> 2;
+        if ((lane & 3) == 0 && (idx >> 2) < cnt) reinterpret_cast<float *>(out + eb)[idx] = val[0];
+        eb += cnt;
+        h = hn;
+    }
+}
+
+}  // namespace
+
+namespace hn {
+namespace quad {
+
+bool supported(const hn_edge_params *p) { return p->hidden == 64 || p->hidden == 128 || p->hidden == 256 || p->hidden == 512; }
+
+int bwd_dst_slices(int hidden) { return hidden == 64 ? 1 : hidden / 128; }
+
+#define HN_QUAD_DISPATCH(KERNEL, ...)                                                         \
+    switch (p->hidden) {                                                                      \
+        case 64: KERNEL<64, 1><<<grid(1), 32 * kWarps, 0, stream>>>(__VA_ARGS__); break;      \
+        case 128: KERNEL<128, 2><<<grid(1), 32 * kWarps, 0, stream>>>(__VA_ARGS__); break;    \
+        case 256: KERNEL<256, 2><<<grid(2), 32 * kWarps, 0, stream>>>(__VA_ARGS__); break;    \
+        default: KERNEL<512, 2><<<grid(4), 32 * kWarps, 0, stream>>>(__VA_ARGS__); break;     \
+    }
+
+int fwd(const hn_edge_params *p, const float *xh, const float *vec, const float *geom, const int32_t *rowptr,
+        const int32_t *col, const int32_t *row_mod, const int64_t *row_xoff, const float *Wt, const float *bias,
+        const float *offset, float *dx, float *dvec, cudaStream_t stream) {
+    auto grid = [&](int ns) { return (unsigned)(((long long)p->n_rows * ns + kWarps - 1) / kWarps); };
+    HN_QUAD_DISPATCH(edge_fwd_quad_kernel, *p, xh, vec, (const float4 *)geom, rowptr, col, row_mod, (const long long *)row_xoff,
+                     Wt, bias, offset, dx, dvec)
+    return 0;
+}
+
+int bwd_dst(const hn_edge_params *p, const float *xh, const float *vec, const float *geom, const int32_t *rowptr,
+            const int32_t *col, const int32_t *row_mod, const int64_t *row_xoff, const float *Wt, const float *bias,
+            const float *offset, const float *g_dx, const float *g_dvec, float *g_geom, int64_t n_edges, cudaStream_t stream) {
+    auto grid = [&](int ns) { return (unsigned)(((long long)p->n_rows * ns + kWarps - 1) / kWarps); };
+    HN_QUAD_DISPATCH(edge_bwd_dst_quad_kernel, *p, xh, vec, (const float4 *)geom, rowptr, col, row_mod,
+                     (const long long *)row_xoff, Wt, bias, offset, g_dx, g_dvec, (float4 *)g_geom, (long long)n_edges)
+    return 0;
+}
+
+}  // namespace quad
+}  // namespace hn

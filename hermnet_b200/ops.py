@@ -242,6 +242,11 @@ def edge_num_slices(hidden: int) -> int:
     return n
 
 
+def edge_set_variant(variant: str) -> None:
+    """'auto': quad-tile edge kernels where supported (F % 64 == 0), 'row': row-per-warp kernels only (A/B measurements)."""
+    _lib.check(_lib.load().hn_painn_edge_set_variant({"auto": 0, "row": 1}[variant]), "hn_painn_edge_set_variant")
+
+
 def painn_edge_fwd(p: EdgeParams, xh, vec, geom, g, Wt, bias, offset):
     lib = _lib.load()
     dev = _chk("painn_edge_fwd", xh, vec, geom, Wt, bias, offset)

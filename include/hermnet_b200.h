@@ -133,7 +133,11 @@ typedef struct {
     float coeff;          /* Gaussian coefficient */
 } hn_edge_params;
 
+/* Planes of g_geom that hn_painn_edge_bwd_dst writes for this F (the caller sums them); 0 = unsupported F. */
 int32_t hn_painn_edge_num_slices(int32_t hidden);
+/* Kernel family behind hn_painn_edge_fwd / _bwd_dst / _bwd_src: 0 = auto (quad-tile kernels for F % 64 == 0, else
+ * row-per-warp), 1 = row-per-warp only (A/B measurements; also selectable with HERMNET_B200_EDGE=row). */
+int hn_painn_edge_set_variant(int32_t variant);
 int hn_painn_edge_fwd(const hn_edge_params *p, const float *xh, const float *vec, const float *geom,
                       const int32_t *rowptr, const int32_t *col, const int32_t *row_mod, const int64_t *row_xoff,
                       const float *Wt, const float *bias, const float *offset, float *dx /*[R,F]*/,

@@ -1,0 +1,126 @@
+"""Quad-tile edge kernels (csrc/hn_edge_quad.cu, the default for F % 64 == 0) against the row-per-warp kernels of
+csrc/hn_edge.cu on identical inputs, and both against a dense float64 evaluation of the reference formula
+(rmnet.py:55-73 with the full K-term Gaussian sum of rmnet.py:168-193).  Covers HVNet / HPNet / HTNet row layouts,
+F = 64 / 128 / 256, small K, rows that are not distance-sorted (graph re-used after the atoms moved, edges crossing the
+cutoff) and rows longer than one tile sweep."""
+import numpy as np
+import pytest
+import torch
+
+from hermnet_b200 import ops
+from tests.test_tiled_plan import _edge_inputs, _model, _system
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    ("HVNet", ["Li", "Al", "Si", "O"], [3, 13, 14, 8], 128, 128, 7),
+    ("HVNet", ["H", "O"], [1, 8], 64, 20, 6),
+    ("HVNet", ["Cr", "Fe", "Ni"], [24, 26, 28], 256, 128, 6),
+    ("HPNet", ["Li", "O"], [3, 8], 64, 50, 6),
+    ("HTNet", ["H", "O"], [1, 8], 128, 128, 6),
+    ("HVNet", ["H", "O"], [1, 8, 6], 128, 32, 6),      # atoms of an element the model does not know: inactive rows
+]
+
+
+def _close(a, b, what, tol):
+    scale = float(b.abs().max()) + 1e-12
+    err = float((a - b).abs().max())
+    assert err <= tol * scale, (what, err, scale)
+
+
+def _run(variant, g, p, geom, xh, vec, Wt, bias, off, g_dx, g_dvec):
+    ops.edge_set_variant(variant)
+    try:
+        dx, dv = ops.painn_edge_fwd(p, xh, vec, geom, g, Wt, bias, off)
+        gg = ops.painn_edge_bwd_dst(p, xh, vec, geom, g, Wt, bias, off, g_dx, g_dvec).sum(0)
+        gxh, gvec = ops.painn_edge_bwd_src(p, xh, vec, geom, g, Wt, bias, off, g_dx, g_dvec)
+    finally:
+        ops.edge_set_variant("auto")
+    return dx, dv, gg, gxh, gvec
+
+
+def _dense_reference(g, p, geom, xh, vec, Wt, bias, off, g_dx, g_dvec):
+    """float64, all K basis functions, autograd for the three gradients."""
+    F = p.hidden
+    dd = lambda t: t.detach().double()
+    xh64, vec64, geom64 = dd(xh).requires_grad_(True), dd(vec).requires_grad_(True), dd(geom).requires_grad_(True)
+    row = g.edge_row.long()
+    mod = g.row_mod.long()[row]
+    live = mod >= 0
+    m = mod.clamp(min=0)
+    u = geom64[:, 3] * float(p.inv_rc)
+    pe = p.env_p
+    a, b, c = -(pe + 1) * (pe + 2) / 2, pe * (pe + 2), -pe * (pe + 1) / 2
+    env = torch.where(u < 1, 1 + a * u ** pe + b * u ** (pe + 1) + c * u ** (pe + 2), torch.zeros_like(u))
+    emb = env[:, None] * torch.exp(float(p.coeff) * (u[:, None] - dd(off)[None, :]) ** 2)
+    phi = torch.einsum("ek,ekc->ec", emb, dd(Wt)[m]) + dd(bias)[m]
+    P = xh64[g.row_xoff.long()[row] + g.col.long()]
+    V = vec64[g.col.long()]
+    A, B, C = torch.split(P * phi, F, dim=-1)
+    mv = (V * (B / 3 ** 0.5)[:, None, :] + C[:, None, :] * geom64[:, :3, None]) / F ** 0.5
+    w = live.double()[:, None]
+    dx = torch.zeros((g.n_rows, F), dtype=torch.float64, device=xh.device).index_add_(0, row, A * w)
+    dv = torch.zeros((g.n_rows, 3, F), dtype=torch.float64, device=xh.device).index_add_(0, row, mv * w[:, :, None])
+    loss = (dx * dd(g_dx)).sum() + (dv * dd(g_dvec)).sum()
+    gxh, gvec, gg = torch.autograd.grad(loss, [xh64, vec64, geom64])
+    return dx.detach(), dv.detach(), gg, gxh, gvec
+
+
+def _compare(model, g, pos, cell, dense=True, tol=2e-5):
+    args = _edge_inputs(model, g, pos, cell)
+    row = _run("row", g, *args)
+    quad = _run("auto", g, *args)
+    names = ("dx", "dvec", "g_geom", "grad_xh", "grad_vec")
+    for n, a, b in zip(names, quad, row):
+        _close(a, b.view_as(a), n + " quad vs row", tol)
+    if dense:
+        ref = _dense_reference(g, *args)
+        for n, a, b, r in zip(names, quad, row, ref):
+            _close(a.double(), r.view_as(a), n + " quad vs float64", tol)
+            # the quad kernels keep the terms the 12-wide band drops: never (materially) worse than the row kernels
+            eq = float((a.double() - r.view_as(a)).abs().max())
+            er = float((b.view_as(a).double() - r.view_as(a)).abs().max())
+            assert eq <= 2.0 * er + 1e-6 * float(r.abs().max()), (n, eq, er)
+
+
+@pytest.mark.parametrize("kind,elems,zs,F,K,n_side", CASES)
+def test_quad_kernels_match_row_kernels_and_float64(kind, elems, zs, F, K, n_side):
+    dev = "cuda:0"
+    pos, Z, cell = _system(n_side, zs, 5)
+    pos, Z, cell = pos.to(dev), Z.to(dev), cell.to(dev)
+    model = _model(kind, elems, F, K, dev)
+    model.builder.tile_plans = model.builder.group_plans = False
+    g = model.build_graph(pos, Z, cell)
+    _compare(model, g, pos, cell)
+
+
+def test_quad_kernels_on_unsorted_rows_and_edges_beyond_the_cutoff():
+    """Graph built for one configuration, kernels run after the atoms moved: rows are no longer distance-sorted (tiles get
+    cut where the union of bands would exceed the table) and some edges lie beyond rc (filter = bias)."""
+    dev = "cuda:0"
+    pos, Z, cell = _system(8, [3, 13, 14, 8], 31)
+    pos, Z, cell = pos.to(dev), Z.to(dev), cell.to(dev)
+    model = _model("HVNet", ["Li", "Al", "Si", "O"], 128, 128, dev)
+    model.builder.tile_plans = model.builder.group_plans = False
+    g = model.build_graph(pos, Z, cell)
+    gen = torch.Generator().manual_seed(1)
+    moved = pos + (torch.rand(pos.shape, generator=gen).to(dev) - 0.5) * 1.6
+    d_new = ops.edge_geom_fwd(moved[g.perm].contiguous(), cell, g)[:, 3]
+    assert int((d_new >= 5.0).sum()) > 100
+    _compare(model, g, moved, cell)
+
+
+def test_quad_kernels_long_rows_dense_system():
+    """rc = 5 on a compressed lattice: ~150 edges per row, many tiles per row."""
+    dev = "cuda:0"
+    rng = np.random.default_rng(3)
+    n_side, a = 8, 1.45
+    grid = np.stack(np.meshgrid(*[np.arange(n_side)] * 3, indexing="ij"), -1).reshape(-1, 3)
+    pos = torch.from_numpy((grid * a + rng.normal(0, 0.05, grid.shape)).astype(np.float32)).to(dev)
+    Z = torch.from_numpy(rng.choice(np.array([1, 8]), size=len(grid))).long().to(dev)
+    cell = torch.from_numpy((np.eye(3) * n_side * a).astype(np.float32)[None]).to(dev)
+    model = _model("HVNet", ["H", "O"], 128, 128, dev)
+    model.builder.tile_plans = model.builder.group_plans = False
+    g = model.build_graph(pos, Z, cell)
+    assert g.n_edges / g.n_atoms > 120
+    _compare(model, g, pos, cell)
