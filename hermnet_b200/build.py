@@ -36,7 +36,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + sources()
+    extra = os.environ.get("HERMNET_B200_NVCC_FLAGS", "").split()      # e.g. -DHN_FWD_PIPE=0 for A/B builds
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + sources()
     subprocess.check_call(cmd)
     return LIB_PATH
 

@@ -510,6 +510,11 @@ extern "C" int hn_painn_edge_bwd_src(const hn_edge_params *p, const float *xh, c
     const char *where = "hn_painn_edge_bwd_src";
     if (int rc = validate(where, p)) return rc;
     if (p->n_atoms <= 0) return 0;
+    if (use_quad(p)) {
+        hn::quad::bwd_src(p, xh, vec, geom, t_rowptr, t_eid, edge_row, row_mod, row_xoff, Wt, bias, offset, g_dx, g_dvec, grad_xh,
+                          grad_vec, (cudaStream_t)stream);
+        return hn::check_launch(where);
+    }
     const int wpb = 8;
     dim3 grid((p->n_atoms + wpb - 1) / wpb, row_slices(p->hidden));
     HN_DISPATCH_VEC(p->hidden, (edge_bwd_src_kernel<VEC><<<grid, 32 * wpb, 0, (cudaStream_t)stream>>>(

@@ -31,6 +31,9 @@ constexpr int kTabW = 64;         // basis functions a tile's union may span
 constexpr int kLo = 5, kHi = 6;   // band = floor(x)-5 .. floor(x)+6, x = u*(K-1)  (same band as hn_edge.cu)
 constexpr int kWarps = 8;
 constexpr int kBig = 1 << 20;
+#ifndef HN_FWD_PIPE
+#define HN_FWD_PIPE 0
+#endif
 
 __device__ __forceinline__ u64 pk(float lo, float hi) {
     u64 r;
@@ -42,6 +45,9 @@ __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
     u64 d;
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
     return d;
+}
+__device__ __forceinline__ void fma2a(u64 &acc, u64 a, u64 b) {    // acc += a * b (in place: spares the allocator a move)
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
 }
 __device__ __forceinline__ u64 mul2(u64 a, u64 b) {
     u64 d;
@@ -65,6 +71,31 @@ __device__ __forceinline__ Pairs<NP> ldp(const float *ptr) {
         r.p[0] = __ldg(reinterpret_cast<const u64 *>(ptr));
     }
     return r;
+}
+
+// Same loads as ordered (volatile) asm: inside the sweeps every filter row is re-loaded IN PLACE right after its last use
+// (the next row's values travel while the remaining FMAs of this row issue), which only works if the compiler keeps the
+// load where it is written.
+template <int NP>
+__device__ __forceinline__ Pairs<NP> ldp_ordered(const float *ptr) {
+    Pairs<NP> r;
+    if constexpr (NP == 2) {
+        asm volatile("ld.global.nc.v2.u64 {%0, %1}, [%2];" : "=l"(r.p[0]), "=l"(r.p[1]) : "l"(ptr));
+    } else {
+        asm volatile("ld.global.nc.u64 %0, [%1];" : "=l"(r.p[0]) : "l"(ptr));
+    }
+    return r;
+}
+__device__ __forceinline__ void lds_pair2(unsigned addr, u64 &a, u64 &b) {
+    asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
+}
+__device__ __forceinline__ void fma2v(u64 &acc, u64 a, u64 b) {   // ordered acc += a * b
+    asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ u64 mul2v(u64 a, u64 b) {
+    u64 d;
+    asm volatile("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
 }
 
 // polynomial envelope (rmnet.py:183-193) and its derivative with respect to u
@@ -225,58 +256,111 @@ edge_fwd_quad_kernel(const hn_edge_params P, const float *__restrict__ xh, const
                         fc[j][n] = bc.p[n];
                     }
             }
-            const float *w = Wm + (size_t)kmin * F3;
-            const float *t = tab;
-            for (u64 mk = mask; mk != 0ull; mk >>= 1, w += F3, t += 2 * T) {
-                if (mk & 1ull) {
-                    const Pairs<NP> wa = ldp<NP>(w), wb = ldp<NP>(w + F), wc = ldp<NP>(w + 2 * F);
-                    u64 gg[T];
-                    load_pairs<T>(t, gg);
+            // sweep the runs of consecutive basis functions of the union mask; software-pipelined in place
+            const unsigned tab_s = (unsigned)__cvta_generic_to_shared(tab);
+            for (u64 mk = mask; mk != 0ull;) {
+                const int k0 = __ffsll((long long)mk) - 1;
+                const u64 inv = ~(mk >> k0);
+                const int len = inv == 0ull ? 64 - k0 : __ffsll((long long)inv) - 1;
+                mk = (k0 + len >= 64) ? 0ull : (mk >> (k0 + len)) << (k0 + len);
+                const float *w = Wm + (size_t)(kmin + k0) * F3;
+                unsigned t = tab_s + k0 * (2 * T * 4);
+                Pairs<NP> wa = ldp_ordered<NP>(w), wb = ldp_ordered<NP>(w + F), wc = ldp_ordered<NP>(w + 2 * F);
+                u64 gg[T];
+                lds_pair2(t, gg[0], gg[1]);
+                lds_pair2(t + 16, gg[2], gg[3]);
+#pragma unroll 1
+                for (int i = 1; i <= len; ++i) {
+                    if (i < len) {       // the last pass re-loads its own row (harmless, stays inside the matrix)
+                        w += F3;
+                        t += 2 * T * 4;
+                    }
 #pragma unroll
                     for (int j = 0; j < T; ++j)
 #pragma unroll
-                        for (int n = 0; n < NP; ++n) {
-                            fa[j][n] = fma2(gg[j], wa.p[n], fa[j][n]);
-                            fb[j][n] = fma2(gg[j], wb.p[n], fb[j][n]);
-                            fc[j][n] = fma2(gg[j], wc.p[n], fc[j][n]);
-                        }
+                        for (int n = 0; n < NP; ++n) fma2v(fa[j][n], gg[j], wa.p[n]);
+                    wa = ldp_ordered<NP>(w);
+#pragma unroll
+                    for (int j = 0; j < T; ++j)
+#pragma unroll
+                        for (int n = 0; n < NP; ++n) fma2v(fb[j][n], gg[j], wb.p[n]);
+                    wb = ldp_ordered<NP>(w + F);
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+#pragma unroll
+                        for (int n = 0; n < NP; ++n) fma2v(fc[j][n], gg[j], wc.p[n]);
+                    lds_pair2(t, gg[0], gg[1]);
+#pragma unroll
+                    for (int j = 2; j < T; ++j)
+#pragma unroll
+                        for (int n = 0; n < NP; ++n) fma2v(fc[j][n], gg[j], wc.p[n]);
+                    wc = ldp_ordered<NP>(w + 2 * F);
+                    lds_pair2(t + 16, gg[2], gg[3]);
                 }
             }
             __syncwarp();    // table reads done before the next tile's fill
+            Pairs<NP> G0[6], G1[6];      // gathered (Pa, Pb, Pc, V0, V1, V2) of the current / next edge
+            float U0[3], U1[3];
+            auto gather = [&](int j, Pairs<NP>(&G)[6], float(&U)[3]) {
+                const int sj = __shfl_sync(kFull, h.s, j);
+                U[0] = __shfl_sync(kFull, h.g.x, j);
+                U[1] = __shfl_sync(kFull, h.g.y, j);
+                U[2] = __shfl_sync(kFull, h.g.z, j);
+                const float *xs = xm + (size_t)sj * F3;
+                const float *vs = vm + (size_t)sj * F3;
+                G[0] = ldp<NP>(xs);
+                G[1] = ldp<NP>(xs + F);
+                G[2] = ldp<NP>(xs + 2 * F);
+                G[3] = ldp<NP>(vs);
+                G[4] = ldp<NP>(vs + F);
+                G[5] = ldp<NP>(vs + 2 * F);
+            };
+            auto fold = [&](int j, const Pairs<NP>(&G)[6], const float(&U)[3]) {
 #pragma unroll
-            for (int j = 0; j < T; ++j) {
-                if (j < cnt) {
-                    const int sj = __shfl_sync(kFull, h.s, j);
-                    const float ux = __shfl_sync(kFull, h.g.x, j), uy = __shfl_sync(kFull, h.g.y, j), uz = __shfl_sync(kFull, h.g.z, j);
-                    const float *xs = xm + (size_t)sj * F3;
-                    const float *vs = vm + (size_t)sj * F3;
-                    const Pairs<NP> Pa = ldp<NP>(xs), Pb = ldp<NP>(xs + F), Pc = ldp<NP>(xs + 2 * F);
-                    const Pairs<NP> V0 = ldp<NP>(vs), V1 = ldp<NP>(vs + F), V2 = ldp<NP>(vs + 2 * F);
+                for (int n = 0; n < NP; ++n) {
+                    float pa[2], pb[2], pc[2], v0[2], v1[2], v2[2], qa[2], qb[2], qc[2];
+                    upk(G[0].p[n], pa[0], pa[1]);
+                    upk(G[1].p[n], pb[0], pb[1]);
+                    upk(G[2].p[n], pc[0], pc[1]);
+                    upk(G[3].p[n], v0[0], v0[1]);
+                    upk(G[4].p[n], v1[0], v1[1]);
+                    upk(G[5].p[n], v2[0], v2[1]);
+                    upk(fa[j][n], qa[0], qa[1]);
+                    upk(fb[j][n], qb[0], qb[1]);
+                    upk(fc[j][n], qc[0], qc[1]);
 #pragma unroll
-                    for (int n = 0; n < NP; ++n) {
-                        float pa[2], pb[2], pc[2], v0[2], v1[2], v2[2], qa[2], qb[2], qc[2];
-                        upk(Pa.p[n], pa[0], pa[1]);
-                        upk(Pb.p[n], pb[0], pb[1]);
-                        upk(Pc.p[n], pc[0], pc[1]);
-                        upk(V0.p[n], v0[0], v0[1]);
-                        upk(V1.p[n], v1[0], v1[1]);
-                        upk(V2.p[n], v2[0], v2[1]);
-                        upk(fa[j][n], qa[0], qa[1]);
-                        upk(fb[j][n], qb[0], qb[1]);
-                        upk(fc[j][n], qc[0], qc[1]);
-#pragma unroll
-                        for (int hh = 0; hh < 2; ++hh) {
-                            const int v = 2 * n + hh;
-                            ax[v] = fmaf(pa[hh], qa[hh], ax[v]);
-                            const float tb = pb[hh] * qb[hh] * c1;
-                            const float tc = pc[hh] * qc[hh] * c2;
-                            av[0][v] += v0[hh] * tb + tc * ux;
-                            av[1][v] += v1[hh] * tb + tc * uy;
-                            av[2][v] += v2[hh] * tb + tc * uz;
-                        }
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const int v = 2 * n + hh;
+                        ax[v] = fmaf(pa[hh], qa[hh], ax[v]);
+                        const float tb = pb[hh] * qb[hh] * c1;
+                        const float tc = pc[hh] * qc[hh] * c2;
+                        av[0][v] += v0[hh] * tb + tc * U[0];
+                        av[1][v] += v1[hh] * tb + tc * U[1];
+                        av[2][v] += v2[hh] * tb + tc * U[2];
                     }
                 }
+            };
+#if HN_FWD_PIPE
+            gather(0, G0, U0);
+            if (cnt > 1) gather(1, G1, U1);
+            fold(0, G0, U0);
+            if (cnt > 1) {
+                if (cnt > 2) gather(2, G0, U0);
+                fold(1, G1, U1);
+                if (cnt > 2) {
+                    if (cnt > 3) gather(3, G1, U1);
+                    fold(2, G0, U0);
+                    if (cnt > 3) fold(3, G1, U1);
+                }
             }
+#else
+#pragma unroll
+            for (int j = 0; j < T; ++j)
+                if (j < cnt) {
+                    gather(j, G0, U0);
+                    fold(j, G0, U0);
+                }
+#endif
             eb += cnt;
             h = hn;
         }
@@ -398,28 +482,50 @@ edge_bwd_dst_quad_kernel(const hn_edge_params P, const float *__restrict__ xh, c
                 qc[j][n] = pk(c_[0], c_[1]);
             }
         }
-        const float *w = Wm + (size_t)kmin * F3;
-        const float *t = tab;
-        for (u64 mk = mask; mk != 0ull; mk >>= 1, w += F3, t += 2 * T) {
-            if (mk & 1ull) {
-                const Pairs<NP> wa = ldp<NP>(w), wb = ldp<NP>(w + F), wc = ldp<NP>(w + 2 * F);
-                u64 gg[T], hh[T];
-                load_pairs<T>(t, gg);
-                load_pairs<T>(t + kTabW * 2 * T, hh);
-#pragma unroll
-                for (int j = 0; j < T; ++j) {
-                    u64 tt = mul2(qa[j][0], wa.p[0]);
-                    tt = fma2(qb[j][0], wb.p[0], tt);
-                    tt = fma2(qc[j][0], wc.p[0], tt);
-                    fc[j][0] = fma2(gg[j], wc.p[0], fc[j][0]);
-                    if constexpr (NP == 2) {
-                        tt = fma2(qa[j][1], wa.p[1], tt);
-                        tt = fma2(qb[j][1], wb.p[1], tt);
-                        tt = fma2(qc[j][1], wc.p[1], tt);
-                        fc[j][1] = fma2(gg[j], wc.p[1], fc[j][1]);
-                    }
-                    ds[j] = fma2(hh[j], tt, ds[j]);
+        const unsigned tab_s = (unsigned)__cvta_generic_to_shared(tab);
+        for (u64 mk = mask; mk != 0ull;) {
+            const int k0 = __ffsll((long long)mk) - 1;
+            const u64 inv = ~(mk >> k0);
+            const int len = inv == 0ull ? 64 - k0 : __ffsll((long long)inv) - 1;
+            mk = (k0 + len >= 64) ? 0ull : (mk >> (k0 + len)) << (k0 + len);
+            const float *w = Wm + (size_t)(kmin + k0) * F3;
+            unsigned t = tab_s + k0 * (2 * T * 4);
+            Pairs<NP> wa = ldp_ordered<NP>(w), wb = ldp_ordered<NP>(w + F), wc = ldp_ordered<NP>(w + 2 * F);
+            u64 gg[T], hh[T];
+            lds_pair2(t, gg[0], gg[1]);
+            lds_pair2(t + kTabW * 2 * T * 4, hh[0], hh[1]);
+#pragma unroll 1
+            for (int i = 1; i <= len; ++i) {
+                if (i < len) {           // the last pass re-loads its own row (harmless, stays inside the matrix)
+                    w += F3;
+                    t += 2 * T * 4;
                 }
+                // per edge and channel pair: tt = qa Wa + qb Wb + qc Wc, then ds += h * tt; fc += g * Wc
+                u64 tt[T][NP];
+#pragma unroll
+                for (int j = 0; j < T; ++j)
+#pragma unroll
+                    for (int n = 0; n < NP; ++n) tt[j][n] = mul2v(qa[j][n], wa.p[n]);
+                wa = ldp_ordered<NP>(w);
+#pragma unroll
+                for (int j = 0; j < T; ++j)
+#pragma unroll
+                    for (int n = 0; n < NP; ++n) fma2v(tt[j][n], qb[j][n], wb.p[n]);
+                wb = ldp_ordered<NP>(w + F);
+#pragma unroll
+                for (int j = 0; j < T; ++j)
+#pragma unroll
+                    for (int n = 0; n < NP; ++n) {
+                        fma2v(tt[j][n], qc[j][n], wc.p[n]);
+                        fma2v(fc[j][n], gg[j], wc.p[n]);
+                    }
+                wc = ldp_ordered<NP>(w + 2 * F);
+                lds_pair2(t, gg[0], gg[1]);
+#pragma unroll
+                for (int j = 0; j < T; ++j)
+#pragma unroll
+                    for (int n = 0; n < NP; ++n) fma2v(ds[j], hh[j], tt[j][n]);
+                lds_pair2(t + kTabW * 2 * T * 4, hh[0], hh[1]);
             }
         }
         __syncwarp();
@@ -475,6 +581,192 @@ edge_bwd_dst_quad_kernel(const hn_edge_params P, const float *__restrict__ xh, c
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// source-major backward over the transposed view (entries of a source sorted by (module, distance)):
+//   grad_xh[m][s] (+=; zero-filled by the caller, each (m, s) row is only touched by the warp that owns s)
+//   grad_vec[s]
+// A source's entries of one sub-network are few (N_neigh / n_modules) and spread over the whole distance range, so
+// their bands barely overlap: one edge per sweep here.  What this kernel changes against edge_bwd_src_kernel is
+// latency, not bytes: the index chain t_eid -> edge_row -> (row_mod, row_xoff) is software-pipelined three entries
+// deep, the 4F gathered gradient values are in flight during the sweep, the filter rows are re-loaded in place, the
+// band values come from a 12-entry shared-memory table (one LDS.64 per basis function instead of a shuffle) and
+// the FMAs are packed.
+// ---------------------------------------------------------------------------------------------------------------
+template <int F, int NP>
+__global__ void __launch_bounds__(32 * kWarps, 2)
+edge_bwd_src_sweep_kernel(const hn_edge_params P, const float *__restrict__ xh, const float *__restrict__ vec,
+                          const float4 *__restrict__ geom, const int *__restrict__ t_rowptr, const int *__restrict__ t_eid,
+                          const int *__restrict__ edge_row, const int *__restrict__ row_mod,
+                          const long long *__restrict__ row_xoff, const float *__restrict__ Wt, const float *__restrict__ bias,
+                          const float *__restrict__ offset, const float *__restrict__ g_dx, const float *__restrict__ g_dvec,
+                          float *__restrict__ grad_xh, float *__restrict__ grad_vec) {
+    constexpr int VEC = 2 * NP, F3 = 3 * F, NS = F / (32 * VEC), NB = kLo + kHi + 1;
+    __shared__ __align__(16) float s_tab[kWarps][2 * 16];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int unit = blockIdx.x * kWarps + warp;
+    const int s = unit / NS, slice = unit % NS;
+    if (s >= P.n_atoms) return;
+    const int K = P.num_rbf;
+    const int ch = slice * (32 * VEC) + lane * VEC;
+    const float c1 = 1.0f / sqrtf(3.0f * (float)F), c2 = 1.0f / sqrtf((float)F);
+    float *tab = s_tab[warp];
+    const unsigned tab_s = (unsigned)__cvta_generic_to_shared(tab);
+    float V[3][VEC], gV[3][VEC], gP[3][VEC], Pb[VEC];
+    {
+        const float *vs = vec + (size_t)s * F3 + ch;
+        const hn::Vec<VEC> a = hn::ldv<VEC>(vs), b = hn::ldv<VEC>(vs + F), c = hn::ldv<VEC>(vs + 2 * F);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            V[0][v] = a.v[v];
+            V[1][v] = b.v[v];
+            V[2][v] = c.v[v];
+            gV[0][v] = gV[1][v] = gV[2][v] = 0.f;
+            gP[0][v] = gP[1][v] = gP[2][v] = 0.f;
+            Pb[v] = 0.f;
+        }
+    }
+    long long cur_off = -1;     // element offset of the xh block the gP accumulators belong to (-1: none)
+    auto flush = [&]() {
+        if (cur_off < 0) return;
+        float *dst = grad_xh + cur_off + (long long)s * F3 + ch;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            hn::Vec<VEC> o = hn::ldv<VEC>(dst + (size_t)k * F);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) {
+                o.v[v] += gP[k][v];
+                gP[k][v] = 0.f;
+            }
+            hn::stv<VEC>(dst + (size_t)k * F, o);
+        }
+    };
+    const int q0 = __ldg(t_rowptr + s), q1 = __ldg(t_rowptr + s + 1);
+    // index pipeline: stage A holds e of entry q+2, stage B (row, geometry) of entry q+1, stage C everything of entry q
+    int eA = -1, rowB = -1, rowC = -1, mC = -1;
+    float4 gB = make_float4(0.f, 0.f, 0.f, 0.f), gC = gB;
+    long long offC = 0;
+    if (q0 < q1) {
+        const int e0 = __ldg(t_eid + q0);
+        rowC = __ldg(edge_row + e0);
+        gC = __ldg(geom + e0);
+        mC = __ldg(row_mod + rowC);
+        offC = __ldg(row_xoff + rowC);
+        if (q0 + 1 < q1) {
+            const int e1 = __ldg(t_eid + q0 + 1);
+            rowB = __ldg(edge_row + e1);
+            gB = __ldg(geom + e1);
+        }
+        if (q0 + 2 < q1) eA = __ldg(t_eid + q0 + 2);
+    }
+    for (int q = q0; q < q1; ++q) {
+        // current entry, then advance the pipeline (loads only; nothing below waits for them before the next pass)
+        const int row = rowC, m = mC;
+        const float4 g = gC;
+        const long long off = offC * F3;
+        int mN = -1;
+        long long offN = 0;
+        if (q + 1 < q1) {
+            mN = __ldg(row_mod + rowB);
+            offN = __ldg(row_xoff + rowB);
+        }
+        const int rowN = rowB;
+        const float4 gN = gB;
+        if (q + 2 < q1) {
+            rowB = __ldg(edge_row + eA);
+            gB = __ldg(geom + eA);
+        }
+        if (q + 3 < q1) eA = __ldg(t_eid + q + 3);
+        if (m >= 0) {
+            if (off != cur_off) {
+                flush();
+                cur_off = off;
+                const hn::Vec<VEC> t = hn::ldv<VEC>(xh + off + (long long)s * F3 + F + ch);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) Pb[v] = t.v[v];
+            }
+            // gathered gradients of the destination row: in flight during the sweep
+            const Pairs<NP> Gx = ldp<NP>(g_dx + (size_t)row * F + ch);
+            const float *gvp = g_dvec + (size_t)row * F3 + ch;
+            const Pairs<NP> G0 = ldp<NP>(gvp), G1 = ldp<NP>(gvp + F), G2 = ldp<NP>(gvp + 2 * F);
+            const float *bm = bias + (size_t)m * F3 + ch;
+            Pairs<NP> fa = ldp<NP>(bm), fb = ldp<NP>(bm + F), fc = ldp<NP>(bm + 2 * F);
+            const float u = g.w * P.inv_rc;
+            if (u < 1.f) {
+                const int kc = (int)(u * (float)(K - 1));
+                const int lo = max(kc - kLo, 0), hi = min(kc + kHi, K - 1);
+                const int len = hi - lo + 1;
+                if (lane < len) {
+                    float env, denv;
+                    envelope<false>(u, P.env_p, env, denv);
+                    const float diff = u - __ldg(offset + lo + lane);
+                    const float val = env * __expf(P.coeff * diff * diff);
+                    *reinterpret_cast<float2 *>(tab + 2 * lane) = make_float2(val, val);
+                }
+                __syncwarp();
+                const float *w = Wt + ((size_t)m * K + lo) * F3 + ch;
+                unsigned t = tab_s;
+                Pairs<NP> wa = ldp_ordered<NP>(w), wb = ldp_ordered<NP>(w + F), wc = ldp_ordered<NP>(w + 2 * F);
+                u64 gg;
+                asm volatile("ld.shared.u64 %0, [%1];" : "=l"(gg) : "r"(t));
+#pragma unroll 1
+                for (int i = 1; i <= len; ++i) {
+                    if (i < len) {       // the last pass re-loads its own row (harmless, stays inside the matrix)
+                        w += F3;
+                        t += 8;
+                    }
+#pragma unroll
+                    for (int n = 0; n < NP; ++n) fma2v(fa.p[n], gg, wa.p[n]);
+                    wa = ldp_ordered<NP>(w);
+#pragma unroll
+                    for (int n = 0; n < NP; ++n) fma2v(fb.p[n], gg, wb.p[n]);
+                    wb = ldp_ordered<NP>(w + F);
+#pragma unroll
+                    for (int n = 0; n < NP; ++n) fma2v(fc.p[n], gg, wc.p[n]);
+                    wc = ldp_ordered<NP>(w + 2 * F);
+                    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(gg) : "r"(t));
+                }
+                __syncwarp();    // table reads done before the next entry's fill
+            }
+#pragma unroll
+            for (int n = 0; n < NP; ++n) {
+                float gx[2], g0[2], g1[2], g2[2], pa[2], pb[2], pc[2];
+                upk(Gx.p[n], gx[0], gx[1]);
+                upk(G0.p[n], g0[0], g0[1]);
+                upk(G1.p[n], g1[0], g1[1]);
+                upk(G2.p[n], g2[0], g2[1]);
+                upk(fa.p[n], pa[0], pa[1]);
+                upk(fb.p[n], pb[0], pb[1]);
+                upk(fc.p[n], pc[0], pc[1]);
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int v = 2 * n + hh;
+                    const float tb = (g0[hh] * V[0][v] + g1[hh] * V[1][v] + g2[hh] * V[2][v]) * c1;
+                    const float tc = (g0[hh] * g.x + g1[hh] * g.y + g2[hh] * g.z) * c2;
+                    gP[0][v] = fmaf(gx[hh], pa[hh], gP[0][v]);
+                    gP[1][v] = fmaf(tb, pb[hh], gP[1][v]);
+                    gP[2][v] = fmaf(tc, pc[hh], gP[2][v]);
+                    const float bphi = Pb[v] * pb[hh] * c1;
+                    gV[0][v] = fmaf(g0[hh], bphi, gV[0][v]);
+                    gV[1][v] = fmaf(g1[hh], bphi, gV[1][v]);
+                    gV[2][v] = fmaf(g2[hh], bphi, gV[2][v]);
+                }
+            }
+        }
+        rowC = rowN;
+        gC = gN;
+        mC = mN;
+        offC = offN;
+    }
+    flush();
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        hn::Vec<VEC> o;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) o.v[v] = gV[k][v];
+        hn::stv<VEC>(grad_vec + (size_t)s * F3 + (size_t)k * F + ch, o);
+    }
+}
+
 }  // namespace
 
 namespace hn {
@@ -507,6 +799,16 @@ int bwd_dst(const hn_edge_params *p, const float *xh, const float *vec, const fl
     auto grid = [&](int ns) { return (unsigned)(((long long)p->n_rows * ns + kWarps - 1) / kWarps); };
     HN_QUAD_DISPATCH(edge_bwd_dst_quad_kernel, *p, xh, vec, (const float4 *)geom, rowptr, col, row_mod,
                      (const long long *)row_xoff, Wt, bias, offset, g_dx, g_dvec, (float4 *)g_geom, (long long)n_edges)
+    return 0;
+}
+
+int bwd_src(const hn_edge_params *p, const float *xh, const float *vec, const float *geom, const int32_t *t_rowptr,
+            const int32_t *t_eid, const int32_t *edge_row, const int32_t *row_mod, const int64_t *row_xoff, const float *Wt,
+            const float *bias, const float *offset, const float *g_dx, const float *g_dvec, float *grad_xh, float *grad_vec,
+            cudaStream_t stream) {
+    auto grid = [&](int ns) { return (unsigned)(((long long)p->n_atoms * ns + kWarps - 1) / kWarps); };
+    HN_QUAD_DISPATCH(edge_bwd_src_sweep_kernel, *p, xh, vec, (const float4 *)geom, t_rowptr, t_eid, edge_row, row_mod,
+                     (const long long *)row_xoff, Wt, bias, offset, g_dx, g_dvec, grad_xh, grad_vec)
     return 0;
 }
 

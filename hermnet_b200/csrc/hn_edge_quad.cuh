@@ -18,5 +18,10 @@ int bwd_dst(const hn_edge_params *p, const float *xh, const float *vec, const fl
             const int32_t *col, const int32_t *row_mod, const int64_t *row_xoff, const float *Wt, const float *bias,
             const float *offset, const float *g_dx, const float *g_dvec, float *g_geom, int64_t n_edges, cudaStream_t stream);
 
+int bwd_src(const hn_edge_params *p, const float *xh, const float *vec, const float *geom, const int32_t *t_rowptr,
+            const int32_t *t_eid, const int32_t *edge_row, const int32_t *row_mod, const int64_t *row_xoff, const float *Wt,
+            const float *bias, const float *offset, const float *g_dx, const float *g_dvec, float *grad_xh, float *grad_vec,
+            cudaStream_t stream);
+
 }  // namespace quad
 }  // namespace hn
