@@ -91,13 +91,19 @@ edge_fwd_kernel(const hn_edge_params P, const float *__restrict__ xh, const floa
                        bc = ldv<VEC>(bias + (size_t)m * F3 + 2 * F + ch);
         const float c1 = 1.0f / sqrtf(3.0f * (float)F), c2 = 1.0f / sqrtf((float)F);
         const int nb = K < kBand ? K : kBand;
+        Vec<VEC> vzero;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) vzero.v[v] = 0.f;
         for (int e = e0; e < e1; ++e) {
             const int s = __ldg(col + e);
             const float4 g = __ldg(geom + e);
             const float *xs = xm + (size_t)s * F3;
-            const float *vs = vec + (size_t)s * F3 + ch;
             const Vec<VEC> Pa = ldv<VEC>(xs), Pb = ldv<VEC>(xs + F), Pc = ldv<VEC>(xs + 2 * F);
-            const Vec<VEC> V0 = ldv<VEC>(vs), V1 = ldv<VEC>(vs + F), V2 = ldv<VEC>(vs + 2 * F);
+            Vec<VEC> V0 = vzero, V1 = vzero, V2 = vzero;
+            if (vec != nullptr) {      // NULL = identically zero (first layer)
+                const float *vs = vec + (size_t)s * F3 + ch;
+                V0 = ldv<VEC>(vs), V1 = ldv<VEC>(vs + F), V2 = ldv<VEC>(vs + 2 * F);
+            }
             Vec<VEC> fa = ba, fb = bb, fc = bc;
             const float u = g.w * P.inv_rc;
             if (u < 1.f) {
@@ -177,9 +183,14 @@ edge_bwd_dst_kernel(const hn_edge_params P, const float *__restrict__ xh, const 
         const int s = __ldg(col + e);
         const float4 g = __ldg(geom + e);
         const float *xs = xm + (size_t)s * F3;
-        const float *vs = vec + (size_t)s * F3 + ch;
         const Vec<VEC> Pa = ldv<VEC>(xs), Pb = ldv<VEC>(xs + F), Pc = ldv<VEC>(xs + 2 * F);
-        const Vec<VEC> V0 = ldv<VEC>(vs), V1 = ldv<VEC>(vs + F), V2 = ldv<VEC>(vs + 2 * F);
+        Vec<VEC> V0, V1, V2;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) V0.v[v] = V1.v[v] = V2.v[v] = 0.f;
+        if (vec != nullptr) {          // NULL = identically zero (first layer)
+            const float *vs = vec + (size_t)s * F3 + ch;
+            V0 = ldv<VEC>(vs), V1 = ldv<VEC>(vs + F), V2 = ldv<VEC>(vs + 2 * F);
+        }
         Vec<VEC> fc = bc, da, db, dc;
 #pragma unroll
         for (int v = 0; v < VEC; ++v) { da.v[v] = 0.f; db.v[v] = 0.f; dc.v[v] = 0.f; }

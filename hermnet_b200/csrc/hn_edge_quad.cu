@@ -211,7 +211,8 @@ __device__ __forceinline__ void load_pairs(const float *tab_row, u64 (&gg)[T]) {
 // ---------------------------------------------------------------------------------------------------------------
 // forward.  One warp = one (row, slice of 64*NP channels); the slices of a row sit in the same CTA.
 // ---------------------------------------------------------------------------------------------------------------
-template <int F, int NP>
+// HV = false: vec is identically zero (first layer, hermnet.py:124): the b part of the filter and the vec gathers vanish.
+template <int F, int NP, bool HV>
 __global__ void __launch_bounds__(32 * kWarps, 2)
 edge_fwd_quad_kernel(const hn_edge_params P, const float *__restrict__ xh, const float *__restrict__ vec,
                      const float4 *__restrict__ geom, const int *__restrict__ rowptr, const int *__restrict__ col,
@@ -252,7 +253,7 @@ edge_fwd_quad_kernel(const hn_edge_params P, const float *__restrict__ xh, const
 #pragma unroll
                     for (int n = 0; n < NP; ++n) {
                         fa[j][n] = ba.p[n];
-                        fb[j][n] = bb.p[n];
+                        fb[j][n] = HV ? bb.p[n] : 0ull;
                         fc[j][n] = bc.p[n];
                     }
             }
@@ -265,7 +266,8 @@ edge_fwd_quad_kernel(const hn_edge_params P, const float *__restrict__ xh, const
                 mk = (k0 + len >= 64) ? 0ull : (mk >> (k0 + len)) << (k0 + len);
                 const float *w = Wm + (size_t)(kmin + k0) * F3;
                 unsigned t = tab_s + k0 * (2 * T * 4);
-                Pairs<NP> wa = ldp_ordered<NP>(w), wb = ldp_ordered<NP>(w + F), wc = ldp_ordered<NP>(w + 2 * F);
+                Pairs<NP> wa = ldp_ordered<NP>(w), wb, wc = ldp_ordered<NP>(w + 2 * F);
+                if constexpr (HV) wb = ldp_ordered<NP>(w + F);
                 u64 gg[T];
                 lds_pair2(t, gg[0], gg[1]);
                 lds_pair2(t + 16, gg[2], gg[3]);
@@ -280,11 +282,13 @@ edge_fwd_quad_kernel(const hn_edge_params P, const float *__restrict__ xh, const
 #pragma unroll
                         for (int n = 0; n < NP; ++n) fma2v(fa[j][n], gg[j], wa.p[n]);
                     wa = ldp_ordered<NP>(w);
+                    if constexpr (HV) {
 #pragma unroll
-                    for (int j = 0; j < T; ++j)
+                        for (int j = 0; j < T; ++j)
 #pragma unroll
-                        for (int n = 0; n < NP; ++n) fma2v(fb[j][n], gg[j], wb.p[n]);
-                    wb = ldp_ordered<NP>(w + F);
+                            for (int n = 0; n < NP; ++n) fma2v(fb[j][n], gg[j], wb.p[n]);
+                        wb = ldp_ordered<NP>(w + F);
+                    }
 #pragma unroll
                     for (int j = 0; j < 2; ++j)
 #pragma unroll
@@ -309,38 +313,49 @@ edge_fwd_quad_kernel(const hn_edge_params P, const float *__restrict__ xh, const
                 const float *xs = xm + (size_t)sj * F3;
                 const float *vs = vm + (size_t)sj * F3;
                 G[0] = ldp<NP>(xs);
-                G[1] = ldp<NP>(xs + F);
                 G[2] = ldp<NP>(xs + 2 * F);
-                G[3] = ldp<NP>(vs);
-                G[4] = ldp<NP>(vs + F);
-                G[5] = ldp<NP>(vs + 2 * F);
+                if constexpr (HV) {
+                    G[1] = ldp<NP>(xs + F);
+                    G[3] = ldp<NP>(vs);
+                    G[4] = ldp<NP>(vs + F);
+                    G[5] = ldp<NP>(vs + 2 * F);
+                }
             };
             auto fold = [&](int j, const Pairs<NP>(&G)[6], const float(&U)[3]) {
 #pragma unroll
                 for (int n = 0; n < NP; ++n) {
-                    float pa[2], pb[2], pc[2], v0[2], v1[2], v2[2], qa[2], qb[2], qc[2];
+                    float pa[2], pb[2] = {0.f, 0.f}, pc[2], v0[2] = {0.f, 0.f}, v1[2] = {0.f, 0.f}, v2[2] = {0.f, 0.f}, qa[2],
+                          qb[2] = {0.f, 0.f}, qc[2];
                     upk(G[0].p[n], pa[0], pa[1]);
-                    upk(G[1].p[n], pb[0], pb[1]);
                     upk(G[2].p[n], pc[0], pc[1]);
-                    upk(G[3].p[n], v0[0], v0[1]);
-                    upk(G[4].p[n], v1[0], v1[1]);
-                    upk(G[5].p[n], v2[0], v2[1]);
                     upk(fa[j][n], qa[0], qa[1]);
-                    upk(fb[j][n], qb[0], qb[1]);
                     upk(fc[j][n], qc[0], qc[1]);
+                    if constexpr (HV) {
+                        upk(G[1].p[n], pb[0], pb[1]);
+                        upk(G[3].p[n], v0[0], v0[1]);
+                        upk(G[4].p[n], v1[0], v1[1]);
+                        upk(G[5].p[n], v2[0], v2[1]);
+                        upk(fb[j][n], qb[0], qb[1]);
+                    }
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
                         const int v = 2 * n + hh;
                         ax[v] = fmaf(pa[hh], qa[hh], ax[v]);
-                        const float tb = pb[hh] * qb[hh] * c1;
                         const float tc = pc[hh] * qc[hh] * c2;
-                        av[0][v] += v0[hh] * tb + tc * U[0];
-                        av[1][v] += v1[hh] * tb + tc * U[1];
-                        av[2][v] += v2[hh] * tb + tc * U[2];
+                        if constexpr (HV) {
+                            const float tb = pb[hh] * qb[hh] * c1;
+                            av[0][v] += v0[hh] * tb + tc * U[0];
+                            av[1][v] += v1[hh] * tb + tc * U[1];
+                            av[2][v] += v2[hh] * tb + tc * U[2];
+                        } else {
+                            av[0][v] = fmaf(tc, U[0], av[0][v]);
+                            av[1][v] = fmaf(tc, U[1], av[1][v]);
+                            av[2][v] = fmaf(tc, U[2], av[2][v]);
+                        }
                     }
                 }
             };
-#if HN_FWD_PIPE
+            if constexpr (!HV || HN_FWD_PIPE) {
             gather(0, G0, U0);
             if (cnt > 1) gather(1, G1, U1);
             fold(0, G0, U0);
@@ -353,14 +368,14 @@ edge_fwd_quad_kernel(const hn_edge_params P, const float *__restrict__ xh, const
                     if (cnt > 3) fold(3, G1, U1);
                 }
             }
-#else
+            } else {
 #pragma unroll
-            for (int j = 0; j < T; ++j)
-                if (j < cnt) {
-                    gather(j, G0, U0);
-                    fold(j, G0, U0);
-                }
-#endif
+                for (int j = 0; j < T; ++j)
+                    if (j < cnt) {
+                        gather(j, G0, U0);
+                        fold(j, G0, U0);
+                    }
+            }
             eb += cnt;
             h = hn;
         }
@@ -386,7 +401,7 @@ edge_fwd_quad_kernel(const hn_edge_params P, const float *__restrict__ xh, const
 // registers per edge); the gathers are issued before the sweep, so their latency hides behind it.  The 8 per-tile
 // partial sums (2 edges x 4 values) are reduced across the warp with a halving exchange (8 shuffles instead of 40).
 // ---------------------------------------------------------------------------------------------------------------
-template <int F, int NP>
+template <int F, int NP, bool HV>
 __global__ void __launch_bounds__(32 * kWarps, 2)
 edge_bwd_dst_quad_kernel(const hn_edge_params P, const float *__restrict__ xh, const float *__restrict__ vec,
                          const float4 *__restrict__ geom, const int *__restrict__ rowptr, const int *__restrict__ col,
@@ -442,11 +457,13 @@ edge_bwd_dst_quad_kernel(const hn_edge_params P, const float *__restrict__ xh, c
             const float *xs = xm + (size_t)sj * F3;
             const float *vs = vm + (size_t)sj * F3;
             Pa[j] = ldp<NP>(xs);
-            Pb[j] = ldp<NP>(xs + F);
             Pc[j] = ldp<NP>(xs + 2 * F);
-            V0[j] = ldp<NP>(vs);
-            V1[j] = ldp<NP>(vs + F);
-            V2[j] = ldp<NP>(vs + 2 * F);
+            if constexpr (HV) {
+                Pb[j] = ldp<NP>(xs + F);
+                V0[j] = ldp<NP>(vs);
+                V1[j] = ldp<NP>(vs + F);
+                V2[j] = ldp<NP>(vs + 2 * F);
+            }
         }
         int kmin;
         u64 mask;
@@ -460,13 +477,15 @@ edge_bwd_dst_quad_kernel(const hn_edge_params P, const float *__restrict__ xh, c
 #pragma unroll
             for (int n = 0; n < NP; ++n) {
                 fc[j][n] = bc.p[n];
-                float pa[2], pb[2], pc[2], v0[2], v1[2], v2[2], a_[2], b_[2], c_[2];
+                float pa[2], pb[2] = {0.f, 0.f}, pc[2], v0[2] = {0.f, 0.f}, v1[2] = {0.f, 0.f}, v2[2] = {0.f, 0.f}, a_[2], b_[2], c_[2];
                 upk(Pa[j].p[n], pa[0], pa[1]);
-                upk(Pb[j].p[n], pb[0], pb[1]);
                 upk(Pc[j].p[n], pc[0], pc[1]);
-                upk(V0[j].p[n], v0[0], v0[1]);
-                upk(V1[j].p[n], v1[0], v1[1]);
-                upk(V2[j].p[n], v2[0], v2[1]);
+                if constexpr (HV) {
+                    upk(Pb[j].p[n], pb[0], pb[1]);
+                    upk(V0[j].p[n], v0[0], v0[1]);
+                    upk(V1[j].p[n], v1[0], v1[1]);
+                    upk(V2[j].p[n], v2[0], v2[1]);
+                }
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh) {
                     const int v = 2 * n + hh;
@@ -490,7 +509,8 @@ edge_bwd_dst_quad_kernel(const hn_edge_params P, const float *__restrict__ xh, c
             mk = (k0 + len >= 64) ? 0ull : (mk >> (k0 + len)) << (k0 + len);
             const float *w = Wm + (size_t)(kmin + k0) * F3;
             unsigned t = tab_s + k0 * (2 * T * 4);
-            Pairs<NP> wa = ldp_ordered<NP>(w), wb = ldp_ordered<NP>(w + F), wc = ldp_ordered<NP>(w + 2 * F);
+            Pairs<NP> wa = ldp_ordered<NP>(w), wb, wc = ldp_ordered<NP>(w + 2 * F);
+            if constexpr (HV) wb = ldp_ordered<NP>(w + F);
             u64 gg[T], hh[T];
             lds_pair2(t, gg[0], gg[1]);
             lds_pair2(t + kTabW * 2 * T * 4, hh[0], hh[1]);
@@ -507,11 +527,13 @@ edge_bwd_dst_quad_kernel(const hn_edge_params P, const float *__restrict__ xh, c
 #pragma unroll
                     for (int n = 0; n < NP; ++n) tt[j][n] = mul2v(qa[j][n], wa.p[n]);
                 wa = ldp_ordered<NP>(w);
+                if constexpr (HV) {
 #pragma unroll
-                for (int j = 0; j < T; ++j)
+                    for (int j = 0; j < T; ++j)
 #pragma unroll
-                    for (int n = 0; n < NP; ++n) fma2v(tt[j][n], qb[j][n], wb.p[n]);
-                wb = ldp_ordered<NP>(w + F);
+                        for (int n = 0; n < NP; ++n) fma2v(tt[j][n], qb[j][n], wb.p[n]);
+                    wb = ldp_ordered<NP>(w + F);
+                }
 #pragma unroll
                 for (int j = 0; j < T; ++j)
 #pragma unroll
@@ -783,13 +805,25 @@ int bwd_dst_slices(int hidden) { return hidden == 64 ? 1 : hidden / 128; }
         case 256: KERNEL<256, 2><<<grid(2), 32 * kWarps, 0, stream>>>(__VA_ARGS__); break;    \
         default: KERNEL<512, 2><<<grid(4), 32 * kWarps, 0, stream>>>(__VA_ARGS__); break;     \
     }
+#define HN_QUAD_DISPATCH_HV(KERNEL, HV, ...)                                                      \
+    switch (p->hidden) {                                                                          \
+        case 64: KERNEL<64, 1, HV><<<grid(1), 32 * kWarps, 0, stream>>>(__VA_ARGS__); break;      \
+        case 128: KERNEL<128, 2, HV><<<grid(1), 32 * kWarps, 0, stream>>>(__VA_ARGS__); break;    \
+        case 256: KERNEL<256, 2, HV><<<grid(2), 32 * kWarps, 0, stream>>>(__VA_ARGS__); break;    \
+        default: KERNEL<512, 2, HV><<<grid(4), 32 * kWarps, 0, stream>>>(__VA_ARGS__); break;     \
+    }
 
 int fwd(const hn_edge_params *p, const float *xh, const float *vec, const float *geom, const int32_t *rowptr,
         const int32_t *col, const int32_t *row_mod, const int64_t *row_xoff, const float *Wt, const float *bias,
         const float *offset, float *dx, float *dvec, cudaStream_t stream) {
     auto grid = [&](int ns) { return (unsigned)(((long long)p->n_rows * ns + kWarps - 1) / kWarps); };
-    HN_QUAD_DISPATCH(edge_fwd_quad_kernel, *p, xh, vec, (const float4 *)geom, rowptr, col, row_mod, (const long long *)row_xoff,
-                     Wt, bias, offset, dx, dvec)
+    if (vec != nullptr) {
+        HN_QUAD_DISPATCH_HV(edge_fwd_quad_kernel, true, *p, xh, vec, (const float4 *)geom, rowptr, col, row_mod,
+                            (const long long *)row_xoff, Wt, bias, offset, dx, dvec)
+    } else {
+        HN_QUAD_DISPATCH_HV(edge_fwd_quad_kernel, false, *p, xh, vec, (const float4 *)geom, rowptr, col, row_mod,
+                            (const long long *)row_xoff, Wt, bias, offset, dx, dvec)
+    }
     return 0;
 }
 
@@ -797,8 +831,13 @@ int bwd_dst(const hn_edge_params *p, const float *xh, const float *vec, const fl
             const int32_t *col, const int32_t *row_mod, const int64_t *row_xoff, const float *Wt, const float *bias,
             const float *offset, const float *g_dx, const float *g_dvec, float *g_geom, int64_t n_edges, cudaStream_t stream) {
     auto grid = [&](int ns) { return (unsigned)(((long long)p->n_rows * ns + kWarps - 1) / kWarps); };
-    HN_QUAD_DISPATCH(edge_bwd_dst_quad_kernel, *p, xh, vec, (const float4 *)geom, rowptr, col, row_mod,
-                     (const long long *)row_xoff, Wt, bias, offset, g_dx, g_dvec, (float4 *)g_geom, (long long)n_edges)
+    if (vec != nullptr) {
+        HN_QUAD_DISPATCH_HV(edge_bwd_dst_quad_kernel, true, *p, xh, vec, (const float4 *)geom, rowptr, col, row_mod,
+                            (const long long *)row_xoff, Wt, bias, offset, g_dx, g_dvec, (float4 *)g_geom, (long long)n_edges)
+    } else {
+        HN_QUAD_DISPATCH_HV(edge_bwd_dst_quad_kernel, false, *p, xh, vec, (const float4 *)geom, rowptr, col, row_mod,
+                            (const long long *)row_xoff, Wt, bias, offset, g_dx, g_dvec, (float4 *)g_geom, (long long)n_edges)
+    }
     return 0;
 }
 

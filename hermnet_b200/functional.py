@@ -117,11 +117,16 @@ class _PaiNNEdge(Function):
     graph has a GroupPlan), tiles (TilePlan, opt-in), row per warp (always available)."""
 
     @staticmethod
-    def forward(ctx, xh, vec, geom, Wt, bias, offset, g: RowGraph, p, coef=None):
+    def forward(ctx, xh, vec, geom, Wt, bias, offset, g: RowGraph, p, coef=None, vec_zero=False):
         xh, vec, geom, Wt, bias = xh.contiguous(), vec.contiguous(), geom.contiguous(), Wt.contiguous(), bias.contiguous()
         ctx.group = coef is not None and g.plan_grp is not None and ops.edge_group_supported(p.hidden, p.num_rbf)
         ctx.tiled = g.plan_dst is not None and ops.edge_tiled_supported(p.hidden, p.num_rbf)
-        if ctx.group:
+        # vec == 0 identically (first layer, hermnet.py:124): the default kernels take NULL and skip the vec gathers and
+        # the F:2F part of the filter in the forward and the destination-major backward
+        ctx.vec_null = bool(vec_zero) and not ctx.group and not ctx.tiled
+        if ctx.vec_null:
+            dx, dvec = ops.painn_edge_fwd(p, xh, None, geom, g, Wt, bias, offset)
+        elif ctx.group:
             dx, dvec = ops.painn_edge_fwd_group(p, xh, vec, _plan_geometry(g, geom)["grp"], g.plan_grp, coef, bias, offset)
         elif ctx.tiled:
             dx, dvec = ops.painn_edge_fwd_tiled(p, xh, vec, _plan_geometry(g, geom)["dst"], g.plan_dst, Wt, bias, offset)
@@ -148,7 +153,7 @@ class _PaiNNEdge(Function):
                 parts = ops.painn_edge_bwd_dst_tiled(p, xh, vec, pg["dst"], g.plan_dst, Wt, bias, offset, g_dx, g_dvec)
                 grad_geom = ops.gather_rows(parts[0] if parts.size(0) == 1 else parts.sum(0), g.plan_dst.pos_of)
             else:
-                parts = ops.painn_edge_bwd_dst(p, xh, vec, geom, g, Wt, bias, offset, g_dx, g_dvec)
+                parts = ops.painn_edge_bwd_dst(p, xh, None if ctx.vec_null else vec, geom, g, Wt, bias, offset, g_dx, g_dvec)
                 grad_geom = parts[0] if parts.size(0) == 1 else parts.sum(0)
         if need[0] or need[1]:
             if ctx.tiled and g.plan_src is not None:
@@ -157,13 +162,14 @@ class _PaiNNEdge(Function):
                 grad_xh, grad_vec = ops.painn_edge_bwd_src(p, xh, vec, geom, g, Wt, bias, offset, g_dx, g_dvec)
         if need[3] or need[4]:
             grad_W, grad_b = ops.painn_edge_bwd_w(p, xh, vec, geom, g, offset, g_dx, g_dvec)
-        return grad_xh, grad_vec, grad_geom, grad_W, grad_b, None, None, None, None
+        return grad_xh, grad_vec, grad_geom, grad_W, grad_b, None, None, None, None, None
 
 
-def painn_edge(xh, vec, geom, Wt, bias, offset, g: RowGraph, p, coef=None):
+def painn_edge(xh, vec, geom, Wt, bias, offset, g: RowGraph, p, coef=None, vec_zero=False):
     """Fused gather -> filter -> message -> segmented reduction.  Returns ``dx [R,F]``, ``dvec [R,3,F]``.
-    ``coef``: piecewise-polynomial table of the filter (filter_table.py) for the row-group kernels."""
-    return _PaiNNEdge.apply(xh, vec, geom, Wt, bias, offset, g, p, coef)
+    ``coef``: piecewise-polynomial table of the filter (filter_table.py) for the row-group kernels.
+    ``vec_zero``: the caller guarantees ``vec == 0`` (first layer); lets the kernels skip everything that multiplies it."""
+    return _PaiNNEdge.apply(xh, vec, geom, Wt, bias, offset, g, p, coef, vec_zero)
 
 
 # ----------------------------------------------------------------------------------------------------

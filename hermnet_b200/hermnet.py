@@ -147,7 +147,7 @@ class _HermNet(nn.Module):
         for li, conv in enumerate(self.hermconvs):
             if halo is not None and li > 0:       # layer 0 reads embeddings / zeros, which every rank has locally
                 x, vec = halo.exchange(x, vec)
-            x, vec = self._layer(conv, x, vec, geom, g, p)
+            x, vec = self._layer(conv, x, vec, geom, g, p, vec_zero=(li == 0))
         tc = fused and self.tensor_core_linear
         h = self.out_energy[1](Fn.linear(x, self.out_energy[0].weight, self.out_energy[0].bias, tc))
         e_atom = self.out_energy[2](h)                                   # [N,1]   hermnet.py:129
@@ -158,7 +158,7 @@ class _HermNet(nn.Module):
         return energy, x, vec
 
     # ------------------------------------------------------------------------------------------------
-    def _layer(self, conv, x, vec, geom, g: RowGraph, p):
+    def _layer(self, conv, x, vec, geom, g: RowGraph, p, vec_zero: bool = False):
         F = self.hidden_channels
         mods = list(conv.mods.values())
         # node side, part 1: projected source features of every sub-network, compact (graph.xh_sources)
@@ -170,7 +170,7 @@ class _HermNet(nn.Module):
             xh = Fn.xproj_hv(x, [m.message_layer for m in mods], mods[0].message_layer.x_layernorm.eps)
             Wt = torch.stack([m.message_layer.rbf_proj.weight.t() for m in mods])
             bias = torch.stack([m.message_layer.rbf_proj.bias for m in mods])
-            dx, dvec = Fn.painn_edge(xh, vec, geom, Wt, bias, self.radial_basis.rbf.offset, g, p, self._filter_table(mods, g))
+            dx, dvec = Fn.painn_edge(xh, vec, geom, Wt, bias, self.radial_basis.rbf.offset, g, p, self._filter_table(mods, g), vec_zero)
             return Fn.node_update_hv(x, vec, dx, dvec, g, mods)
         xhat = torch.nn.functional.layer_norm(x, (F,), None, None, mods[0].message_layer.x_layernorm.eps)
         w1s, b1s = [], []
@@ -198,7 +198,7 @@ class _HermNet(nn.Module):
         bias = torch.stack([m.message_layer.rbf_proj.bias for m in mods])       # [M,3F]
         # edge side
         if p is not None:
-            dx, dvec = Fn.painn_edge(xh, vec, geom, Wt, bias, self.radial_basis.rbf.offset, g, p, self._filter_table(mods, g))
+            dx, dvec = Fn.painn_edge(xh, vec, geom, Wt, bias, self.radial_basis.rbf.offset, g, p, self._filter_table(mods, g), vec_zero)
         else:
             dx, dvec = Fn.painn_edge_composite_flat(xh, vec, geom, Wt, bias, self.radial_basis, g)
         # node side, part 2: residual + update on the destination-element slices

@@ -118,6 +118,8 @@ int hn_edge_geom_bwd(const float *geom, const float *g_geom, int32_t n_parts, co
  * row r reads source s at row (row_xoff[r] + s) of that [rows][3F] buffer (int64 row offsets; for a dense
  * [M][N][3F] layout row_xoff[r] = m*N).  Wt is rbf_proj.weight transposed: [M][K][3F].  gauss_k uses the `offset` buffer (K values,
  * linspace(0,1,K)) and coeff = -0.5/(offset[1]-offset[0])^2; F % 32 == 0.
+ * vec may be NULL in fwd and bwd_dst: vec == 0 identically (the first layer, hermnet.py:124), which removes the vec
+ * gathers and the F:2F part of the filter from those two passes.
  * bwd_dst (row-major pass): g_geom[n_slices][E] = per-edge (dL/du, dL/dd).
  * bwd_src (source-major pass over the transpose): grad_xh (same flat layout as xh; must be zero-filled
  *   by the caller) and grad_vec[N][3][F].

@@ -166,6 +166,8 @@ def _edge_common(p, xh, vec, geom, g, Wt, bias, offset, deriv=False):
 
 
 def painn_edge_fwd(p, xh, vec, geom, g, Wt, bias, offset):
+    if vec is None:                      # NULL = identically zero (include/hermnet_b200.h)
+        vec = torch.zeros((p.n_atoms, 3, p.hidden), dtype=xh.dtype)
     F, row, mm, live, s, P, V, val, phi, _ = _edge_common(p, xh, vec, geom, g, Wt, bias, offset)
     c1, c2 = 1 / math.sqrt(3.0 * F), 1 / math.sqrt(F)
     a, b, c = torch.split(P * phi, F, dim=-1)
@@ -185,6 +187,8 @@ def _t_terms(p, V, geom, g_dvec, row, F):
 
 
 def painn_edge_bwd_dst(p, xh, vec, geom, g, Wt, bias, offset, g_dx, g_dvec):
+    if vec is None:
+        vec = torch.zeros((p.n_atoms, 3, p.hidden), dtype=xh.dtype)
     F, row, mm, live, s, P, V, val, phi, dphi = _edge_common(p, xh, vec, geom, g, Wt, bias, offset, deriv=True)
     gv, tb, tc, c1, c2 = _t_terms(p, V, geom, g_dvec, row, F)
     Pa, Pb, Pc = torch.split(P, F, dim=-1)

@@ -124,3 +124,28 @@ def test_quad_kernels_long_rows_dense_system():
     g = model.build_graph(pos, Z, cell)
     assert g.n_edges / g.n_atoms > 120
     _compare(model, g, pos, cell)
+
+
+@pytest.mark.parametrize("variant", ["auto", "row"])
+@pytest.mark.parametrize("F,K", [(128, 128), (64, 20), (256, 128)])
+def test_null_vec_equals_zero_vec(variant, F, K):
+    """vec = NULL (first layer: vec == 0, hermnet.py:124) must give exactly what a zero tensor gives."""
+    dev = "cuda:0"
+    pos, Z, cell = _system(6, [1, 8], 9)
+    pos, Z, cell = pos.to(dev), Z.to(dev), cell.to(dev)
+    model = _model("HVNet", ["H", "O"], F, K, dev)
+    model.builder.tile_plans = model.builder.group_plans = False
+    g = model.build_graph(pos, Z, cell)
+    p, geom, xh, vec, Wt, bias, off, g_dx, g_dvec = _edge_inputs(model, g, pos, cell)
+    zero = torch.zeros_like(vec)
+    ops.edge_set_variant(variant)
+    try:
+        dx0, dv0 = ops.painn_edge_fwd(p, xh, zero, geom, g, Wt, bias, off)
+        dx1, dv1 = ops.painn_edge_fwd(p, xh, None, geom, g, Wt, bias, off)
+        gg0 = ops.painn_edge_bwd_dst(p, xh, zero, geom, g, Wt, bias, off, g_dx, g_dvec).sum(0)
+        gg1 = ops.painn_edge_bwd_dst(p, xh, None, geom, g, Wt, bias, off, g_dx, g_dvec).sum(0)
+    finally:
+        ops.edge_set_variant("auto")
+    _close(dx1, dx0, "dx", 1e-6)
+    _close(dv1, dv0, "dvec", 1e-6)
+    _close(gg1, gg0, "g_geom", 1e-6)
