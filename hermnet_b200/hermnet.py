@@ -15,6 +15,8 @@ What changed underneath (hermnet.py:37-65,118-152 + utils.py:11-24 + rmnet.py:51
 """
 from __future__ import annotations
 
+import copy
+
 from typing import Dict, List, Optional, Union
 
 import torch
@@ -147,7 +149,7 @@ class _HermNet(nn.Module):
         for li, conv in enumerate(self.hermconvs):
             if halo is not None and li > 0:       # layer 0 reads embeddings / zeros, which every rank has locally
                 x, vec = halo.exchange(x, vec)
-            x, vec = self._layer(conv, x, vec, geom, g, p, vec_zero=(li == 0))
+            x, vec = self._layer(conv, x, vec, geom, g, p, vec_zero=(li == 0), z0=z_i if li == 0 else None)
         tc = fused and self.tensor_core_linear
         h = self.out_energy[1](Fn.linear(x, self.out_energy[0].weight, self.out_energy[0].bias, tc))
         e_atom = self.out_energy[2](h)                                   # [N,1]   hermnet.py:129
@@ -158,7 +160,7 @@ class _HermNet(nn.Module):
         return energy, x, vec
 
     # ------------------------------------------------------------------------------------------------
-    def _layer(self, conv, x, vec, geom, g: RowGraph, p, vec_zero: bool = False):
+    def _layer(self, conv, x, vec, geom, g: RowGraph, p, vec_zero: bool = False, z0=None):
         F = self.hidden_channels
         mods = list(conv.mods.values())
         # node side, part 1: projected source features of every sub-network, compact (graph.xh_sources)
@@ -167,10 +169,24 @@ class _HermNet(nn.Module):
         # reference runs a full LayerNorm pass over all N rows per sub-network (rmnet.py:52).
         if self._fused_node_path(conv, p, g):
             # frozen HVNet parameters on the fused path: hand-written forward/backward for the whole node side
-            xh = Fn.xproj_hv(x, [m.message_layer for m in mods], mods[0].message_layer.x_layernorm.eps)
             Wt = torch.stack([m.message_layer.rbf_proj.weight.t() for m in mods])
             bias = torch.stack([m.message_layer.rbf_proj.bias for m in mods])
-            dx, dvec = Fn.painn_edge(xh, vec, geom, Wt, bias, self.radial_basis.rbf.offset, g, p, self._filter_table(mods, g), vec_zero)
+            if vec_zero and z0 is not None and g.plan_grp is None and g.plan_dst is None:
+                # first layer: x = Embedding[Z] (hermnet.py:123), so the projected source features only depend on the
+                # ELEMENT of the source.  The edge kernels read a [M * n_elements, 3F] table (L1-resident) through an
+                # element-index copy of the column array instead of gathering N distinct rows, and the x_proj GEMMs
+                # shrink from N rows to n_elements rows.  Same arithmetic per row as rmnet.py:52.
+                uniq, col0, xoff0 = self._layer0_tables(g, z0)
+                xs = self.embed(uniq)
+                xh = torch.cat([m.message_layer.node_features(xs) for m in mods], 0)
+                g0 = copy.copy(g)
+                g0.col, g0.row_xoff, g0._lazy = col0, xoff0, {}
+                p0 = ops.EdgeParams(int(uniq.numel()), p.n_rows, p.n_modules, p.hidden, p.num_rbf, p.env_p, p.inv_rc, p.coeff)
+                dx, dvec = Fn.painn_edge(xh, vec, geom, Wt, bias, self.radial_basis.rbf.offset, g0, p0, None, True)
+            else:
+                xh = Fn.xproj_hv(x, [m.message_layer for m in mods], mods[0].message_layer.x_layernorm.eps)
+                dx, dvec = Fn.painn_edge(xh, vec, geom, Wt, bias, self.radial_basis.rbf.offset, g, p, self._filter_table(mods, g),
+                                         vec_zero)
             return Fn.node_update_hv(x, vec, dx, dvec, g, mods)
         xhat = torch.nn.functional.layer_norm(x, (F,), None, None, mods[0].message_layer.x_layernorm.eps)
         w1s, b1s = [], []
@@ -253,6 +269,18 @@ class _HermNet(nn.Module):
             return None
         return filter_table.cached_filter_table([m.message_layer.rbf_proj.weight for m in mods],
                                                 self.radial_basis.rbf.offset, self.radial_basis.rbf.coeff)
+
+    @staticmethod
+    def _layer0_tables(g: RowGraph, z0):
+        """(distinct atomic numbers, element index of every row-edge's source, xh row offset of every row) for the
+        first-layer element table; cached on the graph (the species of a graph never change)."""
+        hit = g._lazy.get("layer0")
+        if hit is None:
+            uniq, inv = torch.unique(z0, return_inverse=True)
+            col0 = inv.to(torch.int32)[g.col.long()].contiguous()
+            xoff0 = (g.row_mod.long().clamp(min=0) * int(uniq.numel())).contiguous()
+            hit = g._lazy["layer0"] = (uniq, col0, xoff0)
+        return hit
 
     def _fused_node_path(self, conv, p, g: RowGraph) -> bool:
         if p is None or not (self.fused_node and self.tensor_core_linear) or self.KIND != "HVNet":
