@@ -43,14 +43,6 @@ SIGNATURES = {
     "hn_painn_edge_bwd_dst": (c_int32, [POINTER(EdgeParams)] + [P] * 13 + [c_int64, P]),
     "hn_painn_edge_bwd_src": (c_int32, [POINTER(EdgeParams)] + [P] * 16),
     "hn_painn_edge_bwd_w": (c_int32, [POINTER(EdgeParams)] + [P] * 12 + [c_int32, P]),
-    "hn_painn_edge_tiled_supported": (c_int32, [c_int32, c_int32]),
-    "hn_painn_edge_tiled_windows": (c_int32, [c_int32]),
-    "hn_painn_edge_fwd_tiled": (c_int32, [POINTER(EdgeParams)] + [P] * 7 + [c_int32, c_int32] + [P] * 6),
-    "hn_painn_edge_bwd_dst_tiled": (c_int32, [POINTER(EdgeParams)] + [P] * 7 + [c_int32, c_int32] + [P] * 6 + [c_int64, P]),
-    "hn_painn_edge_bwd_src_tiled": (c_int32, [POINTER(EdgeParams)] + [P] * 5 + [c_int32, c_int32] + [P] * 8),
-    "hn_painn_edge_group_supported": (c_int32, [c_int32, c_int32]),
-    "hn_painn_edge_fwd_group": (c_int32, [POINTER(EdgeParams)] + [P] * 7 + [c_int32] + [P] * 6),
-    "hn_painn_edge_bwd_dst_group": (c_int32, [POINTER(EdgeParams)] + [P] * 7 + [c_int32] + [P] * 6 + [c_int64, P]),
     "hn_gemm_tf32x3": (c_int32, [P, c_int64, c_int64, c_int64, P, P, c_int64, P, P, c_int64, P]),
     "hn_gemm_tf32x3_ex": (c_int32, [P, c_int64, c_int64, c_int64, P, P, c_int64, P, P, c_int64, c_int32, P, c_int64, P, c_int64, P]),
     "hn_node_pre": (c_int32, [c_int64, c_int32, P, P, c_int64, P, P, c_int64, P, P, P]),

@@ -94,45 +94,18 @@ def edge_geometry(pos: Tensor, cell: Optional[Tensor], g: RowGraph) -> Tensor:
     return _EdgeGeometry.apply(pos, cell, g)
 
 
-def _plan_geometry(g: RowGraph, geom: Tensor):
-    """``geom`` re-ordered into the slot order of the edge plans of the graph, cached on the graph for the tensor object
-    in hand (all layers of one evaluation share it).  Returns a dict with keys 'dst', 'src', 'grp' (present plans)."""
-    hit = g._lazy.get("plan_geom")
-    if hit is not None and hit[0] is geom and hit[1] == geom._version:
-        return hit[2]
-    gd = geom.detach()
-    out = {}
-    if g.plan_dst is not None:
-        out["dst"] = ops.gather_rows(gd, g.plan_dst.eid)
-    if g.plan_src is not None:
-        out["src"] = ops.gather_rows(gd, g.plan_src.eid)
-    if g.plan_grp is not None:
-        out["grp"] = ops.gather_rows(gd, g.plan_grp.eid)
-    g._lazy["plan_geom"] = (geom, geom._version, out)
-    return out
-
-
 class _PaiNNEdge(Function):
-    """Edge side of one layer.  Kernel families, best first: row groups + polynomial filter table (``coef`` given and the
-    graph has a GroupPlan), tiles (TilePlan, opt-in), row per warp (always available)."""
+    """Edge side of one layer: the C ABI picks the tile-sweep kernels (F in {64, 128, 256, 512}) or the row-per-warp
+    kernels (any F % 32 == 0)."""
 
     @staticmethod
-    def forward(ctx, xh, vec, geom, Wt, bias, offset, g: RowGraph, p, coef=None, vec_zero=False):
+    def forward(ctx, xh, vec, geom, Wt, bias, offset, g: RowGraph, p, vec_zero=False):
         xh, vec, geom, Wt, bias = xh.contiguous(), vec.contiguous(), geom.contiguous(), Wt.contiguous(), bias.contiguous()
-        ctx.group = coef is not None and g.plan_grp is not None and ops.edge_group_supported(p.hidden, p.num_rbf)
-        ctx.tiled = g.plan_dst is not None and ops.edge_tiled_supported(p.hidden, p.num_rbf)
-        # vec == 0 identically (first layer, hermnet.py:124): the default kernels take NULL and skip the vec gathers and
-        # the F:2F part of the filter in the forward and the destination-major backward
-        ctx.vec_null = bool(vec_zero) and not ctx.group and not ctx.tiled
-        if ctx.vec_null:
-            dx, dvec = ops.painn_edge_fwd(p, xh, None, geom, g, Wt, bias, offset)
-        elif ctx.group:
-            dx, dvec = ops.painn_edge_fwd_group(p, xh, vec, _plan_geometry(g, geom)["grp"], g.plan_grp, coef, bias, offset)
-        elif ctx.tiled:
-            dx, dvec = ops.painn_edge_fwd_tiled(p, xh, vec, _plan_geometry(g, geom)["dst"], g.plan_dst, Wt, bias, offset)
-        else:
-            dx, dvec = ops.painn_edge_fwd(p, xh, vec, geom, g, Wt, bias, offset)
-        ctx.g, ctx.p, ctx.coef = g, p, coef
+        # vec == 0 identically (first layer, hermnet.py:124): the kernels take NULL and skip the vec gathers and the F:2F
+        # part of the filter in the forward and the destination-major backward
+        ctx.vec_null = bool(vec_zero)
+        dx, dvec = ops.painn_edge_fwd(p, xh, None if ctx.vec_null else vec, geom, g, Wt, bias, offset)
+        ctx.g, ctx.p = g, p
         ctx.save_for_backward(xh, vec, geom, Wt, bias, offset)
         return dx, dvec
 
@@ -144,32 +117,20 @@ class _PaiNNEdge(Function):
         g_dx, g_dvec = g_dx.contiguous(), g_dvec.contiguous()
         need = ctx.needs_input_grad
         grad_xh = grad_vec = grad_geom = grad_W = grad_b = None
-        pg = _plan_geometry(g, geom) if (ctx.group or ctx.tiled) else {}
         if need[2]:
-            if ctx.group:
-                parts = ops.painn_edge_bwd_dst_group(p, xh, vec, pg["grp"], g.plan_grp, ctx.coef, bias, offset, g_dx, g_dvec)
-                grad_geom = ops.gather_rows(parts[0] if parts.size(0) == 1 else parts.sum(0), g.plan_grp.pos_of)
-            elif ctx.tiled:
-                parts = ops.painn_edge_bwd_dst_tiled(p, xh, vec, pg["dst"], g.plan_dst, Wt, bias, offset, g_dx, g_dvec)
-                grad_geom = ops.gather_rows(parts[0] if parts.size(0) == 1 else parts.sum(0), g.plan_dst.pos_of)
-            else:
-                parts = ops.painn_edge_bwd_dst(p, xh, None if ctx.vec_null else vec, geom, g, Wt, bias, offset, g_dx, g_dvec)
-                grad_geom = parts[0] if parts.size(0) == 1 else parts.sum(0)
+            parts = ops.painn_edge_bwd_dst(p, xh, None if ctx.vec_null else vec, geom, g, Wt, bias, offset, g_dx, g_dvec)
+            grad_geom = parts[0] if parts.size(0) == 1 else parts.sum(0)
         if need[0] or need[1]:
-            if ctx.tiled and g.plan_src is not None:
-                grad_xh, grad_vec = ops.painn_edge_bwd_src_tiled(p, xh, vec, pg["src"], g.plan_src, Wt, bias, offset, g_dx, g_dvec)
-            else:
-                grad_xh, grad_vec = ops.painn_edge_bwd_src(p, xh, vec, geom, g, Wt, bias, offset, g_dx, g_dvec)
+            grad_xh, grad_vec = ops.painn_edge_bwd_src(p, xh, vec, geom, g, Wt, bias, offset, g_dx, g_dvec)
         if need[3] or need[4]:
             grad_W, grad_b = ops.painn_edge_bwd_w(p, xh, vec, geom, g, offset, g_dx, g_dvec)
-        return grad_xh, grad_vec, grad_geom, grad_W, grad_b, None, None, None, None, None
+        return grad_xh, grad_vec, grad_geom, grad_W, grad_b, None, None, None, None
 
 
-def painn_edge(xh, vec, geom, Wt, bias, offset, g: RowGraph, p, coef=None, vec_zero=False):
+def painn_edge(xh, vec, geom, Wt, bias, offset, g: RowGraph, p, vec_zero=False):
     """Fused gather -> filter -> message -> segmented reduction.  Returns ``dx [R,F]``, ``dvec [R,3,F]``.
-    ``coef``: piecewise-polynomial table of the filter (filter_table.py) for the row-group kernels.
     ``vec_zero``: the caller guarantees ``vec == 0`` (first layer); lets the kernels skip everything that multiplies it."""
-    return _PaiNNEdge.apply(xh, vec, geom, Wt, bias, offset, g, p, coef, vec_zero)
+    return _PaiNNEdge.apply(xh, vec, geom, Wt, bias, offset, g, p, vec_zero)
 
 
 # ----------------------------------------------------------------------------------------------------

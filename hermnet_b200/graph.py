@@ -47,190 +47,6 @@ def pair_list(n_types: int):
     return [(a, c) for a in range(n_types) for c in range(a, n_types)]
 
 
-TILE_ROWS = 16   # rows (source atoms) per tile of the filter-stationary edge kernels (csrc/hn_edge_tiled.cu: kRT)
-
-
-@dataclass
-class TilePlan:
-    """Bucketed edge order of the tiled edge kernels (csrc/hn_edge_tiled.cu).  Slots are the edges of the plan in
-    (tile, [module,] window) order, every bucket padded to an even count with copies that point at the discarded
-    local row 16.  ``eid[slot]`` is the row-edge a slot was copied from, ``pos_of[e]`` the slot of row-edge ``e``
-    (``n_pad`` for edges of inactive rows)."""
-    n_tiles: int
-    n_windows: int
-    n_pad: int
-    bptr: Tensor                    # int32 [n_tiles * buckets_per_tile + 1]
-    meta: Tensor                    # int32 [n_pad, 4]
-    eid: Tensor                     # int32 [n_pad]
-    pos_of: Tensor                  # int32 [E]
-    tile_rows: Optional[Tensor]     # int32 [n_tiles * 16] (destination plan only)
-    tile_mod: Optional[Tensor]      # int32 [n_tiles]      (destination plan only)
-    covers_all_rows: bool = True
-
-
-def edge_windows(d: Tensor, rc: float, num_rbf: int, n_windows: int) -> Tensor:
-    """Window bucket of every edge: the kernels' ``band_in_window`` rule (band floor(x)-5 .. floor(x)+6 inside
-    [4w, 4w+16)), ``n_windows`` for edges at or beyond the cutoff."""
-    u = d * torch.tensor(1.0 / rc, dtype=torch.float32, device=d.device)
-    kc = torch.floor(u * float(num_rbf - 1)).long()
-    w = torch.div(kc - 5, 4, rounding_mode="floor").clamp_(0, n_windows - 1)
-    return torch.where(u < 1.0, w, torch.full_like(w, n_windows))
-
-
-def _pad_buckets(key: Tensor, n_keys: int):
-    """Stable bucketing by ``key`` (keys == n_keys are dropped) with every bucket padded to an even size.
-    Returns ``bptr int32 [n_keys+1]``, ``eid int64 [n_pad]`` (item copied into each slot), ``real bool [n_pad]``."""
-    dev = key.device
-    rowptr, order = ops.sort_by_key(key.to(torch.int32).contiguous(), n_keys + 1)
-    rowptr = rowptr.long()
-    counts = rowptr[1:n_keys + 1] - rowptr[:n_keys]
-    padded = torch.div(counts + 1, 2, rounding_mode="floor") * 2
-    bptr = torch.zeros(n_keys + 1, dtype=torch.int32, device=dev)
-    torch.cumsum(padded, 0, out=bptr[1:])
-    n_pad = int(bptr[-1].item())
-    if n_pad == 0:
-        return bptr, torch.zeros(0, dtype=torch.long, device=dev), torch.zeros(0, dtype=torch.bool, device=dev)
-    bucket = ops.expand_rowptr(bptr, n_pad).long()
-    k = torch.arange(n_pad, device=dev) - bptr.long()[bucket]
-    cnt = counts[bucket]
-    real = k < cnt
-    eid = order.long()[rowptr[bucket] + torch.minimum(k, cnt - 1)]
-    return bptr, eid, real
-
-
-def build_tile_plans(g: "RowGraph", d: Tensor, rc: float, num_rbf: int):
-    """Destination-major and source-major ``TilePlan`` of a finished ``RowGraph`` (``d`` = current edge lengths)."""
-    n_windows = ops.edge_tiled_windows(num_rbf)
-    if n_windows <= 0 or g.n_edges == 0:
-        return None, None
-    dev = d.device
-    NB = n_windows + 1
-    M = g.n_modules
-    E = g.n_edges
-    rt = TILE_ROWS
-    rm = g.row_mod.long()
-    er = g.edge_row.long()
-    col = g.col.long()
-    win = edge_windows(d, rc, num_rbf, n_windows)
-    xrow = g.row_xoff[er] + col
-    if int(g.xh_base[-1]) >= 2 ** 31:
-        return None, None
-    # ---- destination plan: tiles = 16 active rows of one module ------------------------------------------
-    rows_act = torch.nonzero(rm >= 0).squeeze(1)
-    mods_act = rm[rows_act]
-    o = torch.sort(mods_act, stable=True).indices
-    rows_sorted, mods_sorted = rows_act[o], mods_act[o]
-    cnt_dev = torch.bincount(mods_sorted, minlength=M)
-    cnt = cnt_dev.tolist()
-    tiles_per_mod = [(c + rt - 1) // rt for c in cnt]
-    tile_base, acc = [], 0
-    for t in tiles_per_mod:
-        tile_base.append(acc)
-        acc += t
-    n_tiles = acc
-    mod_start = torch.cumsum(cnt_dev, 0) - cnt_dev
-    r_in_mod = torch.arange(rows_sorted.numel(), device=dev) - mod_start[mods_sorted]
-    slot = torch.tensor(tile_base, dtype=torch.long, device=dev)[mods_sorted] * rt + r_in_mod
-    tile_rows = torch.full((n_tiles * rt,), -1, dtype=torch.int32, device=dev)
-    tile_rows[slot] = rows_sorted.to(torch.int32)
-    tile_mod = torch.repeat_interleave(torch.arange(M, dtype=torch.int32, device=dev),
-                                       torch.tensor(tiles_per_mod, dtype=torch.long, device=dev))
-    slot_of_row = torch.full((g.n_rows,), -1, dtype=torch.long, device=dev)
-    slot_of_row[rows_sorted] = slot
-    es = slot_of_row[er]
-    n_keys = n_tiles * NB
-    key = torch.where(es >= 0, torch.div(es, rt, rounding_mode="floor") * NB + win, torch.full_like(es, n_keys))
-    bptr, eid, real = _pad_buckets(key, n_keys)
-    n_pad = eid.numel()
-    lrow = torch.where(real, es[eid] % rt, torch.full_like(eid, rt))
-    meta = torch.stack([col[eid], lrow, xrow[eid], eid], 1).to(torch.int32).contiguous()
-    pos_of = torch.full((E,), n_pad, dtype=torch.int32, device=dev)
-    pos_of[eid[real]] = torch.arange(n_pad, dtype=torch.int32, device=dev)[real]
-    dst = TilePlan(n_tiles, n_windows, n_pad, bptr, meta, eid.to(torch.int32).contiguous(), pos_of, tile_rows,
-                   tile_mod.contiguous(), covers_all_rows=bool(rows_act.numel() == g.n_rows))
-    # ---- source plan: tiles = 16 consecutive source atoms, buckets (module, window) -----------------------
-    n_tiles_s = (g.n_atoms + rt - 1) // rt
-    em = rm[er]
-    n_keys_s = n_tiles_s * M * NB
-    if n_keys_s >= 2 ** 31 - 2:
-        return dst, None
-    key_s = torch.where(em >= 0, (torch.div(col, rt, rounding_mode="floor") * M + em) * NB + win,
-                        torch.full_like(em, n_keys_s))
-    bptr_s, eid_s, real_s = _pad_buckets(key_s, n_keys_s)
-    n_pad_s = eid_s.numel()
-    lsrc = torch.where(real_s, col[eid_s] % rt, torch.full_like(eid_s, rt))
-    meta_s = torch.stack([er[eid_s], lsrc, xrow[eid_s], eid_s], 1).to(torch.int32).contiguous()
-    pos_of_s = torch.full((E,), n_pad_s, dtype=torch.int32, device=dev)
-    pos_of_s[eid_s[real_s]] = torch.arange(n_pad_s, dtype=torch.int32, device=dev)[real_s]
-    src = TilePlan(n_tiles_s, n_windows, n_pad_s, bptr_s, meta_s, eid_s.to(torch.int32).contiguous(), pos_of_s, None, None)
-    return dst, src
-
-
-GROUP_ROWS = 8   # rows per group of the row-group edge kernels (csrc/hn_edge_group.cu: kGR)
-
-
-@dataclass
-class GroupPlan:
-    """Edge order of the row-group edge kernels: groups of 8 active rows of one sub-network, the group's edges sorted
-    by grid interval of their distance (a performance hint: the kernels re-derive the interval themselves)."""
-    n_groups: int
-    n_slots: int
-    gptr: Tensor         # int32 [n_groups + 1]
-    meta: Tensor         # int32 [n_slots, 4] = (source atom, local row, xh row, interval)
-    eid: Tensor          # int32 [n_slots] row-edge of every slot
-    pos_of: Tensor       # int32 [E] slot of every row-edge (n_slots: edge of an inactive row)
-    group_rows: Tensor   # int32 [n_groups * 8] (-1 = none)
-    group_mod: Tensor    # int32 [n_groups]
-    covers_all_rows: bool = True
-
-
-def build_group_plan(g: "RowGraph", d: Tensor, rc: float, num_rbf: int) -> Optional[GroupPlan]:
-    if g.n_edges == 0 or int(g.xh_base[-1]) >= 2 ** 31:
-        return None
-    dev = d.device
-    M, E, gr, K = g.n_modules, g.n_edges, GROUP_ROWS, num_rbf
-    rm = g.row_mod.long()
-    er = g.edge_row.long()
-    col = g.col.long()
-    u = d * torch.tensor(1.0 / rc, dtype=torch.float32, device=dev)
-    kc = torch.where(u < 1.0, (u * float(K - 1)).long().clamp_(0, K - 2), torch.full_like(er, K - 1))
-    rows_act = torch.nonzero(rm >= 0).squeeze(1)
-    mods_act = rm[rows_act]
-    o = torch.sort(mods_act, stable=True).indices
-    rows_sorted, mods_sorted = rows_act[o], mods_act[o]
-    cnt_dev = torch.bincount(mods_sorted, minlength=M)
-    cnt = cnt_dev.tolist()
-    per_mod = [(c + gr - 1) // gr for c in cnt]
-    base, acc = [], 0
-    for t in per_mod:
-        base.append(acc)
-        acc += t
-    n_groups = acc
-    if n_groups == 0 or n_groups * K >= 2 ** 31 - 2:
-        return None
-    mod_start = torch.cumsum(cnt_dev, 0) - cnt_dev
-    r_in_mod = torch.arange(rows_sorted.numel(), device=dev) - mod_start[mods_sorted]
-    slot = torch.tensor(base, dtype=torch.long, device=dev)[mods_sorted] * gr + r_in_mod
-    group_rows = torch.full((n_groups * gr,), -1, dtype=torch.int32, device=dev)
-    group_rows[slot] = rows_sorted.to(torch.int32)
-    group_mod = torch.repeat_interleave(torch.arange(M, dtype=torch.int32, device=dev),
-                                        torch.tensor(per_mod, dtype=torch.long, device=dev)).contiguous()
-    slot_of_row = torch.full((g.n_rows,), -1, dtype=torch.long, device=dev)
-    slot_of_row[rows_sorted] = slot
-    es = slot_of_row[er]
-    n_keys = n_groups * K
-    key = torch.where(es >= 0, torch.div(es, gr, rounding_mode="floor") * K + kc, torch.full_like(es, n_keys))
-    rowptr, order = ops.sort_by_key(key.to(torch.int32).contiguous(), n_keys + 1)
-    n_slots = int(rowptr[n_keys].item())
-    eid = order.long()[:n_slots]
-    gptr = rowptr[: n_keys + 1: K].contiguous()
-    meta = torch.stack([col[eid], es[eid] % gr, (g.row_xoff[er] + col)[eid], kc[eid]], 1).to(torch.int32).contiguous()
-    pos_of = torch.full((E,), n_slots, dtype=torch.int32, device=dev)
-    pos_of[eid] = torch.arange(n_slots, dtype=torch.int32, device=dev)
-    return GroupPlan(n_groups, n_slots, gptr, meta, eid.to(torch.int32).contiguous(), pos_of, group_rows, group_mod,
-                     covers_all_rows=bool(rows_act.numel() == g.n_rows))
-
-
 class RowGraph:
     def __init__(self):
         self.kind = "HVNet"
@@ -254,9 +70,6 @@ class RowGraph:
         self.own_count: List[int] = []  # per type: number of OWNED atoms (they come first inside the type slice);
         #                                 the rest of the slice are ghost atoms of a domain-decomposed system
         self.energy_index = None      # int32 [N]: graph id of owned atoms, n_graphs for ghosts
-        self.plan_dst: Optional[TilePlan] = None   # bucketed edge orders of the tiled edge kernels (None: row kernels)
-        self.plan_src: Optional[TilePlan] = None
-        self.plan_grp: Optional[GroupPlan] = None  # edge order of the row-group (piecewise-polynomial filter) kernels
         self._lazy = {}
 
     # ---- lazily built segment views (only the differentiable / training formulation needs them) ----------
@@ -324,10 +137,8 @@ class GraphBuilder:
 
     def __init__(self, kind: str, elems: Sequence[str], rc: float, pbc_shift: str = "reference",
                  num_rbf: Optional[int] = None, hidden: Optional[int] = None):
-        self.num_rbf, self.hidden = num_rbf, hidden     # set: also build the TilePlans of the tiled edge kernels
-        # (environment switches: A/B measurements only)
-        self.tile_plans = os.environ.get("HERMNET_B200_TILED", "0") != "0"
-        self.group_plans = os.environ.get("HERMNET_B200_GROUP", "0") != "0"
+        self.num_rbf, self.hidden = num_rbf, hidden
+        # (environment switch: A/B measurements only)
         self.spatial_sort = os.environ.get("HERMNET_B200_SPATIAL", "1") != "0"   # Morton order inside every type slice
         if kind not in ("HVNet", "HPNet", "HTNet"):
             raise ValueError(kind)
@@ -593,12 +404,4 @@ class GraphBuilder:
         cnt.index_add_(0, torch.where(g.row_mod >= 0, g.row_mod.long(), torch.full_like(lens, self.n_modules)), lens)
         g.mod_active = (cnt[: self.n_modules] > 0).to(torch.float32)
         g.mod_active_host = (cnt[: self.n_modules] > 0).tolist()   # (graph build already synchronises)
-        if (self.tile_plans and pos_i is not None and self.num_rbf is not None and self.hidden is not None
-                and g.n_edges > 0 and ops.edge_tiled_supported(self.hidden, self.num_rbf)):
-            d = ops.edge_geom_fwd(pos_i, cell, g)[:, 3].contiguous()
-            g.plan_dst, g.plan_src = build_tile_plans(g, d, self.rc, self.num_rbf)
-        if (self.group_plans and pos_i is not None and self.num_rbf is not None and self.hidden is not None
-                and g.n_edges > 0 and ops.edge_group_supported(self.hidden, self.num_rbf)):
-            d = ops.edge_geom_fwd(pos_i, cell, g)[:, 3].contiguous()
-            g.plan_grp = build_group_plan(g, d, self.rc, self.num_rbf)
         return g

@@ -22,7 +22,6 @@ from typing import Dict, List, Optional, Union
 import torch
 from torch import nn
 
-from . import filter_table
 from . import functional as Fn
 from . import ops
 from .graph import GraphBuilder, RowGraph, pair_list
@@ -171,7 +170,7 @@ class _HermNet(nn.Module):
             # frozen HVNet parameters on the fused path: hand-written forward/backward for the whole node side
             Wt = torch.stack([m.message_layer.rbf_proj.weight.t() for m in mods])
             bias = torch.stack([m.message_layer.rbf_proj.bias for m in mods])
-            if vec_zero and z0 is not None and g.plan_grp is None and g.plan_dst is None:
+            if vec_zero and z0 is not None:
                 # first layer: x = Embedding[Z] (hermnet.py:123), so the projected source features only depend on the
                 # ELEMENT of the source.  The edge kernels read a [M * n_elements, 3F] table (L1-resident) through an
                 # element-index copy of the column array instead of gathering N distinct rows, and the x_proj GEMMs
@@ -182,11 +181,10 @@ class _HermNet(nn.Module):
                 g0 = copy.copy(g)
                 g0.col, g0.row_xoff, g0._lazy = col0, xoff0, {}
                 p0 = ops.EdgeParams(int(uniq.numel()), p.n_rows, p.n_modules, p.hidden, p.num_rbf, p.env_p, p.inv_rc, p.coeff)
-                dx, dvec = Fn.painn_edge(xh, vec, geom, Wt, bias, self.radial_basis.rbf.offset, g0, p0, None, True)
+                dx, dvec = Fn.painn_edge(xh, vec, geom, Wt, bias, self.radial_basis.rbf.offset, g0, p0, True)
             else:
                 xh = Fn.xproj_hv(x, [m.message_layer for m in mods], mods[0].message_layer.x_layernorm.eps)
-                dx, dvec = Fn.painn_edge(xh, vec, geom, Wt, bias, self.radial_basis.rbf.offset, g, p, self._filter_table(mods, g),
-                                         vec_zero)
+                dx, dvec = Fn.painn_edge(xh, vec, geom, Wt, bias, self.radial_basis.rbf.offset, g, p, vec_zero)
             return Fn.node_update_hv(x, vec, dx, dvec, g, mods)
         xhat = torch.nn.functional.layer_norm(x, (F,), None, None, mods[0].message_layer.x_layernorm.eps)
         w1s, b1s = [], []
@@ -214,7 +212,7 @@ class _HermNet(nn.Module):
         bias = torch.stack([m.message_layer.rbf_proj.bias for m in mods])       # [M,3F]
         # edge side
         if p is not None:
-            dx, dvec = Fn.painn_edge(xh, vec, geom, Wt, bias, self.radial_basis.rbf.offset, g, p, self._filter_table(mods, g), vec_zero)
+            dx, dvec = Fn.painn_edge(xh, vec, geom, Wt, bias, self.radial_basis.rbf.offset, g, p, vec_zero)
         else:
             dx, dvec = Fn.painn_edge_composite_flat(xh, vec, geom, Wt, bias, self.radial_basis, g)
         # node side, part 2: residual + update on the destination-element slices
@@ -262,13 +260,6 @@ class _HermNet(nn.Module):
         if n_unknown:
             pad(n_unknown)
         return torch.cat(xs, 0), torch.cat(vs, 0)
-
-    def _filter_table(self, mods, g: RowGraph):
-        """Polynomial table of every sub-network's radial filter for the row-group edge kernels (None: no GroupPlan)."""
-        if g.plan_grp is None:
-            return None
-        return filter_table.cached_filter_table([m.message_layer.rbf_proj.weight for m in mods],
-                                                self.radial_basis.rbf.offset, self.radial_basis.rbf.coeff)
 
     @staticmethod
     def _layer0_tables(g: RowGraph, z0):

@@ -304,106 +304,6 @@ def painn_edge_bwd_w(p: EdgeParams, xh, vec, geom, g, offset, g_dx, g_dvec):
 
 
 # ----------------------------------------------------------------------------------------------------
-# tiled (filter-stationary) edge kernels: same contract as the three functions above, driven by a graph.TilePlan
-# ----------------------------------------------------------------------------------------------------
-def edge_tiled_supported(hidden: int, num_rbf: int) -> bool:
-    return bool(_lib.load().hn_painn_edge_tiled_supported(int(hidden), int(num_rbf)))
-
-
-def edge_tiled_windows(num_rbf: int) -> int:
-    return int(_lib.load().hn_painn_edge_tiled_windows(int(num_rbf)))
-
-
-def painn_edge_fwd_tiled(p: EdgeParams, xh, vec, geom_b, plan, Wt, bias, offset):
-    lib = _lib.load()
-    dev = _chk("painn_edge_fwd_tiled", xh, vec, geom_b, Wt, bias, offset, plan.bptr, plan.meta, plan.tile_rows, plan.tile_mod)
-    _f32("painn_edge_fwd_tiled", xh, vec, geom_b, Wt, bias, offset)
-    _i32("painn_edge_fwd_tiled", plan.bptr, plan.meta, plan.tile_rows, plan.tile_mod)
-    F = p.hidden
-    alloc = torch.empty if plan.covers_all_rows else torch.zeros
-    dx = alloc((p.n_rows, F), dtype=torch.float32, device=dev)
-    dvec = alloc((p.n_rows, 3, F), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev), _timed("painn_edge_fwd", dev):
-        _lib.check(lib.hn_painn_edge_fwd_tiled(ctypes.byref(p), _ptr(xh), _ptr(vec), _ptr(geom_b), _ptr(plan.bptr),
-                                               _ptr(plan.meta), _ptr(plan.tile_rows), _ptr(plan.tile_mod), plan.n_tiles,
-                                               plan.n_windows, _ptr(Wt), _ptr(bias), _ptr(offset), _ptr(dx), _ptr(dvec),
-                                               _stream(dev)), "hn_painn_edge_fwd_tiled")
-    return dx, dvec
-
-
-def painn_edge_bwd_dst_tiled(p: EdgeParams, xh, vec, geom_b, plan, Wt, bias, offset, g_dx, g_dvec):
-    """Per-slot ``(dL/du, dL/dd)`` partials ``[hidden/64, n_pad + 1, 4]`` in plan order; the extra last slot is zero
-    (``plan.pos_of`` sends the edges of inactive rows there)."""
-    lib = _lib.load()
-    dev = _chk("painn_edge_bwd_dst_tiled", xh, vec, geom_b, Wt, bias, offset, g_dx, g_dvec)
-    _f32("painn_edge_bwd_dst_tiled", xh, vec, geom_b, Wt, bias, offset, g_dx, g_dvec)
-    ns = p.hidden // 64
-    out = torch.empty((ns, plan.n_pad + 1, 4), dtype=torch.float32, device=dev)
-    out[:, plan.n_pad].zero_()
-    with torch.cuda.device(dev), _timed("painn_edge_bwd_dst", dev):
-        _lib.check(lib.hn_painn_edge_bwd_dst_tiled(ctypes.byref(p), _ptr(xh), _ptr(vec), _ptr(geom_b), _ptr(plan.bptr),
-                                                   _ptr(plan.meta), _ptr(plan.tile_rows), _ptr(plan.tile_mod), plan.n_tiles,
-                                                   plan.n_windows, _ptr(Wt), _ptr(bias), _ptr(offset), _ptr(g_dx),
-                                                   _ptr(g_dvec), _ptr(out), plan.n_pad + 1, _stream(dev)),
-                   "hn_painn_edge_bwd_dst_tiled")
-    return out
-
-
-def painn_edge_bwd_src_tiled(p: EdgeParams, xh, vec, geom_s, plan, Wt, bias, offset, g_dx, g_dvec):
-    lib = _lib.load()
-    dev = _chk("painn_edge_bwd_src_tiled", xh, vec, geom_s, Wt, bias, offset, g_dx, g_dvec)
-    _f32("painn_edge_bwd_src_tiled", xh, vec, geom_s, Wt, bias, offset, g_dx, g_dvec)
-    grad_xh = torch.zeros_like(xh)
-    grad_vec = torch.empty_like(vec)
-    with torch.cuda.device(dev), _timed("painn_edge_bwd_src", dev):
-        _lib.check(lib.hn_painn_edge_bwd_src_tiled(ctypes.byref(p), _ptr(xh), _ptr(vec), _ptr(geom_s), _ptr(plan.bptr),
-                                                   _ptr(plan.meta), plan.n_tiles, plan.n_windows, _ptr(Wt), _ptr(bias),
-                                                   _ptr(offset), _ptr(g_dx), _ptr(g_dvec), _ptr(grad_xh), _ptr(grad_vec),
-                                                   _stream(dev)), "hn_painn_edge_bwd_src_tiled")
-    return grad_xh, grad_vec
-
-
-# ----------------------------------------------------------------------------------------------------
-# row-group edge kernels with the piecewise-polynomial filter table (graph.GroupPlan, filter_table.py)
-# ----------------------------------------------------------------------------------------------------
-def edge_group_supported(hidden: int, num_rbf: int) -> bool:
-    return bool(_lib.load().hn_painn_edge_group_supported(int(hidden), int(num_rbf)))
-
-
-def painn_edge_fwd_group(p: EdgeParams, xh, vec, geom_g, plan, coef, bias, offset):
-    lib = _lib.load()
-    dev = _chk("painn_edge_fwd_group", xh, vec, geom_g, coef, bias, offset, plan.gptr, plan.meta, plan.group_rows, plan.group_mod)
-    _f32("painn_edge_fwd_group", xh, vec, geom_g, coef, bias, offset)
-    _i32("painn_edge_fwd_group", plan.gptr, plan.meta, plan.group_rows, plan.group_mod)
-    F = p.hidden
-    alloc = torch.empty if plan.covers_all_rows else torch.zeros
-    dx = alloc((p.n_rows, F), dtype=torch.float32, device=dev)
-    dvec = alloc((p.n_rows, 3, F), dtype=torch.float32, device=dev)
-    with torch.cuda.device(dev), _timed("painn_edge_fwd", dev):
-        _lib.check(lib.hn_painn_edge_fwd_group(ctypes.byref(p), _ptr(xh), _ptr(vec), _ptr(geom_g), _ptr(plan.gptr), _ptr(plan.meta),
-                                               _ptr(plan.group_rows), _ptr(plan.group_mod), plan.n_groups, _ptr(coef), _ptr(bias),
-                                               _ptr(offset), _ptr(dx), _ptr(dvec), _stream(dev)), "hn_painn_edge_fwd_group")
-    return dx, dvec
-
-
-def painn_edge_bwd_dst_group(p: EdgeParams, xh, vec, geom_g, plan, coef, bias, offset, g_dx, g_dvec):
-    """Per-slot ``(dL/du, dL/dd)`` partials ``[hidden/64, n_slots + 1, 4]``; the extra last slot is zero
-    (``plan.pos_of`` sends the edges of inactive rows there)."""
-    lib = _lib.load()
-    dev = _chk("painn_edge_bwd_dst_group", xh, vec, geom_g, coef, bias, offset, g_dx, g_dvec)
-    _f32("painn_edge_bwd_dst_group", xh, vec, geom_g, coef, bias, offset, g_dx, g_dvec)
-    ns = p.hidden // 64
-    out = torch.empty((ns, plan.n_slots + 1, 4), dtype=torch.float32, device=dev)
-    out[:, plan.n_slots].zero_()
-    with torch.cuda.device(dev), _timed("painn_edge_bwd_dst", dev):
-        _lib.check(lib.hn_painn_edge_bwd_dst_group(ctypes.byref(p), _ptr(xh), _ptr(vec), _ptr(geom_g), _ptr(plan.gptr),
-                                                   _ptr(plan.meta), _ptr(plan.group_rows), _ptr(plan.group_mod), plan.n_groups,
-                                                   _ptr(coef), _ptr(bias), _ptr(offset), _ptr(g_dx), _ptr(g_dvec), _ptr(out),
-                                                   plan.n_slots + 1, _stream(dev)), "hn_painn_edge_bwd_dst_group")
-    return out
-
-
-# ----------------------------------------------------------------------------------------------------
 # gather / segmented sum
 # ----------------------------------------------------------------------------------------------------
 def gather_rows(X: Tensor, idx: Tensor) -> Tensor:

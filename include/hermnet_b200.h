@@ -165,63 +165,6 @@ int hn_painn_edge_bwd_w(const hn_edge_params *p, const float *xh, const float *v
                         void *stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Tiled ("filter-stationary") variants of the three edge kernels above -- same arithmetic, same
- * reference lines (rmnet.py:55-73, 168-193), different loop nest: rows (bwd_src: source atoms) are
- * grouped in tiles of 16 of one sub-network and the edges of a tile are bucketed by the 16-wide window
- * [4w, 4w+16) of basis functions containing their Gaussian band, so one
- * warp keeps the window's filter rows in registers and streams the bucket through them.
- *   n_windows = hn_painn_edge_tiled_windows(K); every tile has (n_windows + 1) buckets, the last one
- *   holding edges with d >= rc (filter = bias).  Buckets are padded to an even number of slots.
- *   bptr  int32 [n_tiles * B + 1], B = n_windows + 1 (bwd_src: B = M * (n_windows + 1), module-major)
- *   meta  int32 [n_slots][4]: fwd/bwd_dst = (source atom, local row 0..15 | 16 = discard, xh row, -)
- *                            bwd_src     = (destination row, local source 0..15 | 16, xh row, -)
- *   geom_b float [n_slots][4]: (ux, uy, uz, d) of every slot (bucket order)
- *   tile_rows int32 [n_tiles][16] row ids (-1 = none), tile_mod int32 [n_tiles]
- * fwd writes dx/dvec only for rows listed in tile_rows; bwd_dst writes g_geom_b[hidden/64][n_pad][4]
- * in slot order; bwd_src needs grad_xh zero-filled and writes every grad_vec row.
- * The kernels re-derive each edge's band from its current distance and fall back to a per-edge
- * evaluation when the bucket does not cover it (plan built for older positions).
- * Requires hidden % 64 == 0, 64 <= hidden <= 512, num_rbf >= 16 (hn_painn_edge_tiled_supported).
- * ------------------------------------------------------------------------------------------- */
-int32_t hn_painn_edge_tiled_supported(int32_t hidden, int32_t num_rbf);
-int32_t hn_painn_edge_tiled_windows(int32_t num_rbf);
-int hn_painn_edge_fwd_tiled(const hn_edge_params *p, const float *xh, const float *vec, const float *geom_b,
-                            const int32_t *bptr, const int32_t *meta, const int32_t *tile_rows,
-                            const int32_t *tile_mod, int32_t n_tiles, int32_t n_windows, const float *Wt,
-                            const float *bias, const float *offset, float *dx, float *dvec, void *stream);
-int hn_painn_edge_bwd_dst_tiled(const hn_edge_params *p, const float *xh, const float *vec, const float *geom_b,
-                                const int32_t *bptr, const int32_t *meta, const int32_t *tile_rows,
-                                const int32_t *tile_mod, int32_t n_tiles, int32_t n_windows, const float *Wt,
-                                const float *bias, const float *offset, const float *g_dx, const float *g_dvec,
-                                float *g_geom_b, int64_t n_pad, void *stream);
-int hn_painn_edge_bwd_src_tiled(const hn_edge_params *p, const float *xh, const float *vec, const float *geom_s,
-                                const int32_t *bptr, const int32_t *meta, int32_t n_tiles, int32_t n_windows,
-                                const float *Wt, const float *bias, const float *offset, const float *g_dx,
-                                const float *g_dvec, float *grad_xh /*zeroed*/, float *grad_vec, void *stream);
-
-/* ---------------------------------------------------------------------------------------------
- * Row-group variants of fwd / bwd_dst with a piecewise-polynomial radial filter -- same arithmetic and
- * reference lines as hn_painn_edge_fwd / _bwd_dst.  coef [M][K-1][10][3F] tabulates, per grid interval
- * kc of offset[], the degree-9 polynomial in s = 2 (d/rc - offset[kc]) (K-1) - 1 of
- * sum_k W[m][k][c] gauss_k (built in fp64 by hermnet_b200/filter_table.py; accuracy 8e-8 of max).
- * Rows are grouped by 8 (one sub-network per group); slots [gptr[g], gptr[g+1]) of group g are its
- * edges sorted by interval: meta[slot] = (source atom, local row 0..7, xh row, interval), geom_g[slot] =
- * (ux,uy,uz,d); group_rows int32 [n_groups][8] (-1 = none), group_mod int32 [n_groups].
- * fwd writes dx/dvec for the rows listed in group_rows; bwd_dst writes g_geom_g[hidden/64][n_slots][4].
- * Requires hidden % 64 == 0, 64 <= hidden <= 512 (hn_painn_edge_group_supported).
- * ------------------------------------------------------------------------------------------- */
-int32_t hn_painn_edge_group_supported(int32_t hidden, int32_t num_rbf);
-int hn_painn_edge_fwd_group(const hn_edge_params *p, const float *xh, const float *vec, const float *geom_g,
-                            const int32_t *gptr, const int32_t *meta, const int32_t *group_rows,
-                            const int32_t *group_mod, int32_t n_groups, const float *coef, const float *bias,
-                            const float *offset, float *dx, float *dvec, void *stream);
-int hn_painn_edge_bwd_dst_group(const hn_edge_params *p, const float *xh, const float *vec, const float *geom_g,
-                                const int32_t *gptr, const int32_t *meta, const int32_t *group_rows,
-                                const int32_t *group_mod, int32_t n_groups, const float *coef, const float *bias,
-                                const float *offset, const float *g_dx, const float *g_dvec, float *g_geom_g,
-                                int64_t n_slots, void *stream);
-
-/* ---------------------------------------------------------------------------------------------
  * Row gather / segmented sum -- mutually adjoint linear primitives used by the differentiable
  * (double-backward, training) formulation.  Replace PyG's index_select gathers (rmnet.py:58) and
  * torch_scatter.scatter's atomicAdd (rmnet.py:71-72, hermnet.py:130) with deterministic kernels.

@@ -230,181 +230,6 @@ def painn_edge_bwd_w(p, xh, vec, geom, g, offset, g_dx, g_dvec):
     return gW, gb
 
 
-# ---- tiled (filter-stationary) edge kernels: slot-by-slot emulation of csrc/hn_edge_tiled.cu -------------------
-def edge_tiled_supported(hidden, num_rbf):
-    return hidden % 64 == 0 and 64 <= hidden <= 512 and num_rbf >= 16
-
-
-def edge_tiled_windows(num_rbf):
-    return 0 if num_rbf < 16 else (num_rbf - 16 + 3) // 4 + 1
-
-
-def _slot_values(p, geom_b, offset, wi, NW, deriv=False):
-    """env*g_k per slot the way the tiled kernels evaluate it: the whole 16-wide window when it covers the edge's band,
-    the 12-term fallback when it does not (stale plan), nothing beyond the cutoff."""
-    K = p.num_rbf
-    u = geom_b[:, 3] * p.inv_rc
-    kc = torch.floor(u * (K - 1)).long()
-    lo, hi = (kc - 5).clamp(min=0), (kc + 6).clamp(max=K - 1)
-    k0 = torch.minimum(4 * wi, torch.full_like(wi, K - 16))
-    in_range = wi < NW
-    covered = in_range & (k0 <= lo) & (hi <= k0 + 15)
-    k = torch.arange(K)[None, :]
-    win = (k >= k0[:, None]) & (k < k0[:, None] + 16)
-    fb0 = (kc - 5).clamp(min=0).clamp(max=K - 12)
-    band = (k >= fb0[:, None]) & (k < fb0[:, None] + 12)
-    use = torch.where(covered[:, None], win, band) & (u < 1)[:, None]
-    pp = p.env_p
-    a, b, c = -0.5 * (pp + 1) * (pp + 2), float(pp * (pp + 2)), -0.5 * pp * (pp + 1)
-    env = 1 + a * u ** pp + b * u ** (pp + 1) + c * u ** (pp + 2)
-    diff = u[:, None] - offset[None, :]
-    gk = torch.exp(p.coeff * diff * diff)
-    val = torch.where(use, env[:, None] * gk, torch.zeros_like(gk))
-    if not deriv:
-        return val, None
-    denv = a * pp * u ** (pp - 1) + b * (pp + 1) * u ** pp + c * (pp + 2) * u ** (pp + 1)
-    dval = (denv[:, None] * gk + env[:, None] * gk * (2 * p.coeff * diff)) * p.inv_rc
-    return val, torch.where(use, dval, torch.zeros_like(dval))
-
-
-def _dst_slots(p, plan):
-    NB = plan.n_windows + 1
-    bucket = _rows(plan.bptr)
-    assert bucket.numel() == plan.n_pad and (plan.bptr[1:] - plan.bptr[:-1]).remainder(2).eq(0).all()
-    tile, wi = bucket // NB, bucket % NB
-    meta = plan.meta.long()
-    src, lrow, xrow = meta[:, 0], meta[:, 1], meta[:, 2]
-    real = lrow < 16
-    row = plan.tile_rows.long()[(tile * 16 + lrow.clamp(max=15))]
-    assert (row[real] >= 0).all()
-    m = plan.tile_mod.long()[tile]
-    return wi, src, xrow, real, row.clamp(min=0), m
-
-
-def painn_edge_fwd_tiled(p, xh, vec, geom_b, plan, Wt, bias, offset):
-    F = p.hidden
-    wi, src, xrow, real, row, m = _dst_slots(p, plan)
-    val, _ = _slot_values(p, geom_b, offset, wi, plan.n_windows)
-    phi = torch.einsum("ek,ekc->ec", val, Wt[m]) + bias[m]
-    c1, c2 = 1 / math.sqrt(3.0 * F), 1 / math.sqrt(F)
-    a, b, c = torch.split(xh[xrow] * phi, F, dim=-1)
-    mv = vec[src] * (b * c1)[:, None, :] + (c * c2)[:, None, :] * geom_b[:, :3, None]
-    lv = real.to(xh.dtype)
-    dx = torch.zeros((p.n_rows, F), dtype=xh.dtype).index_add_(0, row, a * lv[:, None])
-    dvec = torch.zeros((p.n_rows, 3, F), dtype=xh.dtype).index_add_(0, row, mv * lv[:, None, None])
-    return dx, dvec
-
-
-def painn_edge_bwd_dst_tiled(p, xh, vec, geom_b, plan, Wt, bias, offset, g_dx, g_dvec):
-    F = p.hidden
-    wi, src, xrow, real, row, m = _dst_slots(p, plan)
-    val, dval = _slot_values(p, geom_b, offset, wi, plan.n_windows, deriv=True)
-    phi = torch.einsum("ek,ekc->ec", val, Wt[m]) + bias[m]
-    dphi = torch.einsum("ek,ekc->ec", dval, Wt[m])
-    P, V = xh[xrow], vec[src]
-    gv, tb, tc, c1, c2 = _t_terms(p, V, geom_b, g_dvec, row, F)
-    Pa, Pb, Pc = torch.split(P, F, dim=-1)
-    da, db, dc = torch.split(dphi, F, dim=-1)
-    gd = (g_dx[row] * Pa * da + tb * Pb * db + tc * Pc * dc).sum(1)
-    cphi = Pc * phi[:, 2 * F:] * c2
-    gu = (gv * cphi[:, None, :]).sum(2)
-    out = torch.zeros((F // 64, plan.n_pad + 1, 4), dtype=xh.dtype)
-    out[0, :plan.n_pad] = torch.cat([gu, gd[:, None]], 1) * real.to(xh.dtype)[:, None]
-    return out
-
-
-def painn_edge_bwd_src_tiled(p, xh, vec, geom_s, plan, Wt, bias, offset, g_dx, g_dvec):
-    F, M = p.hidden, p.n_modules
-    NB = plan.n_windows + 1
-    bucket = _rows(plan.bptr)
-    assert bucket.numel() == plan.n_pad and (plan.bptr[1:] - plan.bptr[:-1]).remainder(2).eq(0).all()
-    tile, m, wi = bucket // (M * NB), (bucket // NB) % M, bucket % NB
-    meta = plan.meta.long()
-    row, lsrc, xrow = meta[:, 0], meta[:, 1], meta[:, 2]
-    real = lsrc < 16
-    s = (tile * 16 + lsrc.clamp(max=15)).clamp(max=p.n_atoms - 1)
-    val, _ = _slot_values(p, geom_s, offset, wi, plan.n_windows)
-    phi = torch.einsum("ek,ekc->ec", val, Wt[m]) + bias[m]
-    P, V = xh[xrow], vec[s]
-    gv, tb, tc, c1, c2 = _t_terms(p, V, geom_s, g_dvec, row, F)
-    fa, fb, fc = torch.split(phi, F, dim=-1)
-    lv = real.to(xh.dtype)[:, None]
-    gP = torch.cat([g_dx[row] * fa, tb * fb, tc * fc], 1) * lv
-    grad_xh = torch.zeros_like(xh).index_add_(0, xrow, gP)
-    bphi = P[:, F:2 * F] * fb * c1 * lv
-    grad_vec = torch.zeros_like(vec).index_add_(0, s, gv * bphi[:, None, :])
-    return grad_xh, grad_vec
-
-
-# ---- row-group kernels with the piecewise-polynomial filter table: slot-by-slot emulation of csrc/hn_edge_group.cu ----
-def edge_group_supported(hidden, num_rbf):
-    return hidden % 64 == 0 and 64 <= hidden <= 512 and num_rbf >= 2
-
-
-def _poly_phi(p, geom_g, coef, bias, offset, m, deriv=False):
-    """phi (and dphi/dd) per slot the way the group kernels evaluate them (Horner on the table, float32)."""
-    K = p.num_rbf
-    u = geom_g[:, 3] * torch.tensor(p.inv_rc, dtype=torch.float32)
-    live = u < 1
-    kc = (u * float(K - 1)).long().clamp(0, K - 2)
-    s = (2.0 * (K - 1)) * (u - offset[kc]) - 1.0
-    c = coef[m, kc]                                           # [E, 10, 3F]
-    pv = c[:, -1]
-    qv = torch.zeros_like(pv)
-    for n in range(c.size(1) - 2, -1, -1):
-        qv = qv * s[:, None] + pv
-        pv = pv * s[:, None] + c[:, n]
-    pp = p.env_p
-    a, b, cc = -0.5 * (pp + 1) * (pp + 2), float(pp * (pp + 2)), -0.5 * pp * (pp + 1)
-    env = 1 + a * u ** pp + b * u ** (pp + 1) + cc * u ** (pp + 2)
-    lv = live.to(pv.dtype)[:, None]
-    phi = bias[m] + env[:, None] * pv * lv
-    if not deriv:
-        return phi, None
-    denv = a * pp * u ** (pp - 1) + b * (pp + 1) * u ** pp + cc * (pp + 2) * u ** (pp + 1)
-    dphi = (denv[:, None] * pv + env[:, None] * qv * (2.0 * (K - 1))) * p.inv_rc * lv
-    return phi, dphi
-
-
-def _grp_slots(plan):
-    lens = (plan.gptr[1:] - plan.gptr[:-1]).long()
-    group = torch.repeat_interleave(torch.arange(plan.n_groups), lens)
-    assert group.numel() == plan.n_slots
-    meta = plan.meta.long()
-    src, lrow, xrow = meta[:, 0], meta[:, 1], meta[:, 2]
-    row = plan.group_rows.long()[group * 8 + lrow]
-    assert (row >= 0).all()
-    return src, xrow, row, plan.group_mod.long()[group]
-
-
-def painn_edge_fwd_group(p, xh, vec, geom_g, plan, coef, bias, offset):
-    F = p.hidden
-    src, xrow, row, m = _grp_slots(plan)
-    phi, _ = _poly_phi(p, geom_g, coef, bias, offset, m)
-    c1, c2 = 1 / math.sqrt(3.0 * F), 1 / math.sqrt(F)
-    a, b, c = torch.split(xh[xrow] * phi, F, dim=-1)
-    mv = vec[src] * (b * c1)[:, None, :] + (c * c2)[:, None, :] * geom_g[:, :3, None]
-    dx = torch.zeros((p.n_rows, F), dtype=xh.dtype).index_add_(0, row, a)
-    dvec = torch.zeros((p.n_rows, 3, F), dtype=xh.dtype).index_add_(0, row, mv)
-    return dx, dvec
-
-
-def painn_edge_bwd_dst_group(p, xh, vec, geom_g, plan, coef, bias, offset, g_dx, g_dvec):
-    F = p.hidden
-    src, xrow, row, m = _grp_slots(plan)
-    phi, dphi = _poly_phi(p, geom_g, coef, bias, offset, m, deriv=True)
-    P, V = xh[xrow], vec[src]
-    gv, tb, tc, c1, c2 = _t_terms(p, V, geom_g, g_dvec, row, F)
-    Pa, Pb, Pc = torch.split(P, F, dim=-1)
-    da, db, dc = torch.split(dphi, F, dim=-1)
-    gd = (g_dx[row] * Pa * da + tb * Pb * db + tc * Pc * dc).sum(1)
-    cphi = Pc * phi[:, 2 * F:] * c2
-    gu = (gv * cphi[:, None, :]).sum(2)
-    out = torch.zeros((F // 64, plan.n_slots + 1, 4), dtype=xh.dtype)
-    out[0, :plan.n_slots] = torch.cat([gu, gd[:, None]], 1)
-    return out
-
-
 def gather_rows(X, idx):
     return X[idx.long()].contiguous()
 
@@ -504,9 +329,7 @@ def install(monkeypatch):
     """Swap ``hermnet_b200.ops`` for the CPU emulation (pytest ``monkeypatch`` restores it afterwards)."""
     for name in ("radius_graph", "sort_by_key", "expand_rowptr", "triplets", "triplet_dots", "edge_geom_fwd",
                  "edge_geom_bwd", "edge_params", "edge_num_slices", "painn_edge_fwd", "painn_edge_bwd_dst",
-                 "painn_edge_bwd_src", "painn_edge_bwd_w", "edge_tiled_supported", "edge_tiled_windows", "painn_edge_fwd_tiled",
-                 "painn_edge_bwd_dst_tiled", "painn_edge_bwd_src_tiled", "edge_group_supported", "painn_edge_fwd_group",
-                 "painn_edge_bwd_dst_group", "gemm_tf32x3_ex", "node_pre", "node_mid", "node_post",
+                 "painn_edge_bwd_src", "painn_edge_bwd_w", "gemm_tf32x3_ex", "node_pre", "node_mid", "node_post",
                  "node_post_bwd", "node_mid_bwd", "node_pre_bwd", "gather_rows", "segment_sum", "gemm_tf32x3", "split_tf32"):
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(ops, "require_cuda", lambda t, what: None)

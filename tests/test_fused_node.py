@@ -6,7 +6,7 @@ import torch
 
 import hermnet_b200 as H
 from tests import util
-from tests.test_tiled_plan import _system
+from tests.util import lattice_system as _system
 
 
 def _run(model, pos, Z, cell, fused_node):

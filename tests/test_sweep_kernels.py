@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from hermnet_b200 import ops
-from tests.test_tiled_plan import _edge_inputs, _model, _system
+from tests.util import edge_inputs as _edge_inputs, frozen_model as _model, lattice_system as _system
 
 pytestmark = pytest.mark.gpu
 
@@ -89,7 +89,6 @@ def test_quad_kernels_match_row_kernels_and_float64(kind, elems, zs, F, K, n_sid
     pos, Z, cell = _system(n_side, zs, 5)
     pos, Z, cell = pos.to(dev), Z.to(dev), cell.to(dev)
     model = _model(kind, elems, F, K, dev)
-    model.builder.tile_plans = model.builder.group_plans = False
     g = model.build_graph(pos, Z, cell)
     _compare(model, g, pos, cell)
 
@@ -101,7 +100,6 @@ def test_quad_kernels_on_unsorted_rows_and_edges_beyond_the_cutoff():
     pos, Z, cell = _system(8, [3, 13, 14, 8], 31)
     pos, Z, cell = pos.to(dev), Z.to(dev), cell.to(dev)
     model = _model("HVNet", ["Li", "Al", "Si", "O"], 128, 128, dev)
-    model.builder.tile_plans = model.builder.group_plans = False
     g = model.build_graph(pos, Z, cell)
     gen = torch.Generator().manual_seed(1)
     moved = pos + (torch.rand(pos.shape, generator=gen).to(dev) - 0.5) * 1.6
@@ -120,7 +118,6 @@ def test_quad_kernels_long_rows_dense_system():
     Z = torch.from_numpy(rng.choice(np.array([1, 8]), size=len(grid))).long().to(dev)
     cell = torch.from_numpy((np.eye(3) * n_side * a).astype(np.float32)[None]).to(dev)
     model = _model("HVNet", ["H", "O"], 128, 128, dev)
-    model.builder.tile_plans = model.builder.group_plans = False
     g = model.build_graph(pos, Z, cell)
     assert g.n_edges / g.n_atoms > 120
     _compare(model, g, pos, cell)
@@ -134,7 +131,6 @@ def test_null_vec_equals_zero_vec(variant, F, K):
     pos, Z, cell = _system(6, [1, 8], 9)
     pos, Z, cell = pos.to(dev), Z.to(dev), cell.to(dev)
     model = _model("HVNet", ["H", "O"], F, K, dev)
-    model.builder.tile_plans = model.builder.group_plans = False
     g = model.build_graph(pos, Z, cell)
     p, geom, xh, vec, Wt, bias, off, g_dx, g_dvec = _edge_inputs(model, g, pos, cell)
     zero = torch.zeros_like(vec)

@@ -6,6 +6,7 @@ import numpy as np
 import torch
 
 import hermnet_b200 as H
+from hermnet_b200 import ops
 from oracle import hermnet_oracle as O
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -63,3 +64,36 @@ def energy_forces(model, data):
 
 def rel_err(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp(min=1e-30))
+
+
+# ---- synthetic lattice systems / frozen models / random edge-kernel inputs shared by the kernel-level tests ----------
+def lattice_system(n_side, elems_z, seed, a=2.3, jitter=0.1):
+    rng = np.random.default_rng(seed)
+    g = np.stack(np.meshgrid(*[np.arange(n_side)] * 3, indexing="ij"), -1).reshape(-1, 3).astype(np.float64)
+    pos = (g * a + rng.normal(0, jitter, g.shape)).astype(np.float32)
+    Z = rng.choice(np.array(elems_z), size=len(pos))
+    cell = (np.eye(3) * n_side * a).astype(np.float32)[None]
+    return torch.from_numpy(pos), torch.from_numpy(Z).long(), torch.from_numpy(cell)
+
+
+def frozen_model(kind, elems, F, K, dev, layers=2, seed=7):
+    torch.manual_seed(seed)
+    m = getattr(H, kind)(elems=elems, rc=5.0, num_layers=layers, hidden_channels=F, num_rbf=K).to(dev).eval()
+    for p in m.parameters():
+        p.requires_grad_(False)
+    return m
+
+
+def edge_inputs(model, g, pos, cell, seed=3):
+    F, K = model.hidden_channels, model.num_rbf
+    dev = pos.device
+    gen = torch.Generator().manual_seed(seed)
+    rn = lambda *s: torch.randn(*s, generator=gen).to(dev)
+    geom = ops.edge_geom_fwd(pos[g.perm].contiguous(), cell, g)
+    xh = rn(g.xh_base[-1], 3 * F)
+    vec = rn(g.n_atoms, 3, F)
+    Wt = rn(g.n_modules, K, 3 * F) / np.sqrt(K)
+    bias = rn(g.n_modules, 3 * F)
+    g_dx, g_dvec = rn(g.n_rows, F), rn(g.n_rows, 3, F)
+    p = ops.edge_params(g, g.n_modules, F, K, int(model.radial_basis.envelope.p), model.rc, model.radial_basis.rbf.coeff)
+    return p, geom, xh, vec, Wt, bias, model.radial_basis.rbf.offset, g_dx, g_dvec
