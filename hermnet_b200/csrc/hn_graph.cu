@@ -431,11 +431,41 @@ SortWs carve_sort(void *base, int64_t n, int32_t n_keys) {
     return w;
 }
 
+// Histogram of the keys (+ the identity permutation the radix sort carries along).  One global atomic per ITEM
+// serialises on hot counters (256 distance bins for 3.6e7 edges took 4 ms per call), so:
+//   few keys  -> per-CTA histogram in shared memory, flushed once per CTA;
+//   many keys -> lanes of a warp holding the same key are merged with __match_any_sync before the global atomic.
+constexpr int kHistItems = 16;          // items per thread of the shared-memory variant
+constexpr int kHistSmallKeys = 8192;
+
+__global__ void __launch_bounds__(256)
+key_hist_small_kernel(const int *__restrict__ keys, int64_t n, int n_keys, int *iota, int *count) {
+    extern __shared__ int s_hist[];
+    for (int k = threadIdx.x; k < n_keys; k += blockDim.x) s_hist[k] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * (blockDim.x * kHistItems);
+#pragma unroll 4
+    for (int j = 0; j < kHistItems; ++j) {
+        const int64_t i = base + (int64_t)j * blockDim.x + threadIdx.x;
+        if (i < n) {
+            iota[i] = (int)i;
+            atomicAdd(&s_hist[keys[i]], 1);
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < n_keys; k += blockDim.x) {
+        const int c = s_hist[k];
+        if (c != 0) atomicAdd(&count[k], c);
+    }
+}
+
 __global__ void key_hist_kernel(const int *__restrict__ keys, int64_t n, int *iota, int *count) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    iota[i] = (int)i;
-    atomicAdd(&count[keys[i]], 1);
+    const bool live = i < n;
+    const int key = live ? keys[i] : -1;
+    if (live) iota[i] = (int)i;
+    const unsigned peers = __match_any_sync(0xffffffffu, key);
+    if (live && (__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&count[key], __popc(peers));
 }
 
 __global__ void expand_rowptr_kernel(const int *__restrict__ rowptr, int n_rows, int *edge_row) {
@@ -460,7 +490,15 @@ extern "C" int hn_sort_by_key(const int32_t *keys, int64_t n, int32_t n_keys, in
     SortWs w = carve_sort(workspace, n < 1 ? 1 : n, n_keys);
     HN_REQUIRE(workspace_bytes >= w.total, where, "workspace too small");
     HN_CUDA(cudaMemsetAsync(w.count, 0, 4 * ((int64_t)n_keys + 2), st), where);
-    if (n > 0) key_hist_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(keys, n, w.iota, w.count);
+    if (n > 0) {
+        if (n_keys <= kHistSmallKeys) {
+            const int64_t per_cta = 256 * kHistItems;
+            key_hist_small_kernel<<<(int)((n + per_cta - 1) / per_cta), 256, (size_t)n_keys * sizeof(int), st>>>(keys, n, n_keys,
+                                                                                                                 w.iota, w.count);
+        } else {
+            key_hist_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(keys, n, w.iota, w.count);
+        }
+    }
     size_t bytes = w.cub_bytes;
     HN_CUDA(cub::DeviceScan::ExclusiveSum(w.cub_temp, bytes, w.count, rowptr, n_keys + 1, st), where);
     if (n > 0) {

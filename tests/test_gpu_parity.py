@@ -288,3 +288,20 @@ def test_ase_style_calculator_md_and_batched_displacements():
     for k, p in enumerate(disp):
         atoms.positions = p.astype(np.float64)
         assert float(np.abs(fb[k] - atoms.get_forces()).max()) < TOL_F * max(1.0, float(np.abs(fb[k]).max()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,n_keys", [(0, 5), (1, 1), (1000, 7), (300000, 256), (300000, 8192), (300000, 8193), (500000, 400000)])
+def test_sort_by_key_is_a_stable_counting_sort(n, n_keys):
+    """hn_sort_by_key (shared-memory histogram for few keys, warp-aggregated atomics for many) == stable argsort."""
+    from hermnet_b200 import ops
+    gen = torch.Generator().manual_seed(n + n_keys)
+    keys = torch.randint(0, n_keys, (n,), generator=gen, dtype=torch.int32)
+    if n > 10:
+        keys[: n // 3] = keys[: n // 3].sort().values        # sorted stretch: many equal keys inside a warp
+    rowptr, order = ops.sort_by_key(keys.to(DEV), n_keys)
+    ref_order = torch.sort(keys.long(), stable=True).indices
+    ref_ptr = torch.zeros(n_keys + 1, dtype=torch.long)
+    ref_ptr[1:] = torch.cumsum(torch.bincount(keys.long(), minlength=n_keys), 0)
+    assert torch.equal(rowptr.cpu().long(), ref_ptr)
+    assert torch.equal(order.cpu().long(), ref_order)
