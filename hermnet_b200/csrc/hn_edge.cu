@@ -16,9 +16,9 @@
 // function k0+j (one expf per lane per edge), broadcast by shuffle.  The graph builder sorts every row by
 // distance (and every transposed row by (module, distance)), so consecutive edges of a warp hit mostly the
 // same W rows in L1.
-// Tried and rejected (round 1): 4-edge register tiles sharing each W row over the union of the bands -- fewer
-// L1 bytes but ~1.7x more issued instructions (union window 22 vs 12, shuffle+select per (edge,k)); measured
-// 60/66/138 ms vs 35/42/81 ms per launch at 1M atoms.
+// These row kernels are the fallback for F % 32 == 0 outside {64, 128, 256, 512} and the A/B partner of the tile-sweep
+// kernels of hn_edge_quad.cu, which share one band sweep between consecutive edges of a row and are the default
+// (hn_painn_edge_set_variant / HERMNET_B200_EDGE=row selects these).
 #include <cstdlib>
 #include <cstring>
 
