@@ -3,7 +3,8 @@ sys.path.insert(0, os.getcwd())
 import numpy as np
 import hermnet_b200 as H
 from hermnet_b200 import synthetic, ops
-(pos, Z, cell), cfg = synthetic.config("C4", 1.0)
+name = sys.argv[1] if len(sys.argv) > 1 else "C4"
+(pos, Z, cell), cfg = synthetic.config(name, 1.0)
 kind = cfg.pop("kind")
 torch.manual_seed(1234)
 dev = torch.device("cuda:0")
@@ -20,3 +21,4 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     g = model.build_graph(pos_d, Z_d, cell_d, None)
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=60))
+print(prof.key_averages().table(sort_by="self_cpu_time_total", row_limit=15, max_name_column_width=60))
