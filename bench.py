@@ -174,6 +174,8 @@ def main():
     args = parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "C5":      # 30 rows per atom: 20 GB tensors; avoid losing tens of GB to allocator fragmentation
+        os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

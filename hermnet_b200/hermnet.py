@@ -21,6 +21,7 @@ from typing import Dict, List, Optional, Union
 
 import torch
 from torch import nn
+from torch.utils.checkpoint import checkpoint as torch_checkpoint
 
 from . import functional as Fn
 from . import ops
@@ -66,6 +67,9 @@ class _HermNet(nn.Module):
         self.tensor_core_linear = True   # fused path: node-side nn.Linear layers run on tcgen05 (3xTF32 split)
         self.fused_node = True           # frozen HVNet parameters: fused node-side kernels with hand-written backward
         self.store_features = False   # write data.x / data.vec back like the reference does (hermnet.py:63-64)
+        # None: recompute every layer in the backward pass instead of keeping its activations (torch.utils.checkpoint)
+        # when the per-layer edge-side tensors of all layers would not fit the device; True / False force it
+        self.checkpoint_layers: Optional[bool] = None
 
         self.embed = nn.Embedding(len(atomic_numbers), hidden_channels)
         self.radial_basis = RadialBasis(num_radial=num_rbf, cutoff=rc, rbf=rbf, envelope=envelope)
@@ -145,10 +149,15 @@ class _HermNet(nn.Module):
             p = None
         x = self.embed(z_i)
         vec = torch.zeros((x.size(0), 3, F), dtype=x.dtype, device=x.device)
+        ckpt = self._want_checkpoint(g, pos) if self.checkpoint_layers is None else bool(self.checkpoint_layers)
         for li, conv in enumerate(self.hermconvs):
             if halo is not None and li > 0:       # layer 0 reads embeddings / zeros, which every rank has locally
                 x, vec = halo.exchange(x, vec)
-            x, vec = self._layer(conv, x, vec, geom, g, p, vec_zero=(li == 0), z0=z_i if li == 0 else None)
+            if ckpt and torch.is_grad_enabled():
+                x, vec = torch_checkpoint(self._layer, conv, x, vec, geom, g, p, vec_zero=(li == 0),
+                                          z0=z_i if li == 0 else None, ckpt=True, use_reentrant=False)
+            else:
+                x, vec = self._layer(conv, x, vec, geom, g, p, vec_zero=(li == 0), z0=z_i if li == 0 else None)
         tc = fused and self.tensor_core_linear
         h = self.out_energy[1](Fn.linear(x, self.out_energy[0].weight, self.out_energy[0].bias, tc))
         e_atom = self.out_energy[2](h)                                   # [N,1]   hermnet.py:129
@@ -159,7 +168,7 @@ class _HermNet(nn.Module):
         return energy, x, vec
 
     # ------------------------------------------------------------------------------------------------
-    def _layer(self, conv, x, vec, geom, g: RowGraph, p, vec_zero: bool = False, z0=None):
+    def _layer(self, conv, x, vec, geom, g: RowGraph, p, vec_zero: bool = False, z0=None, ckpt: bool = False):
         F = self.hidden_channels
         mods = list(conv.mods.values())
         # node side, part 1: projected source features of every sub-network, compact (graph.xh_sources)
@@ -208,6 +217,7 @@ class _HermNet(nn.Module):
                 ml = mod.message_layer
                 blocks.append(lin(ml.x_proj[1](Fn.linear(rows, w1, b1, tc)), ml.x_proj[2]))
         xh = torch.cat(blocks, 0)                                        # [rows, 3F]
+        del blocks
         Wt = torch.stack([m.message_layer.rbf_proj.weight.t() for m in mods])   # [M,K,3F]
         bias = torch.stack([m.message_layer.rbf_proj.bias for m in mods])       # [M,3F]
         # edge side
@@ -226,40 +236,67 @@ class _HermNet(nn.Module):
             xs.append(torch.zeros((n_rows, F), dtype=x.dtype, device=x.device))
             vs.append(torch.zeros((n_rows, 3, F), dtype=x.dtype, device=x.device))
 
+        def update_type(t, xt, vt, dxt, dvt):
+            """Sum over the sub-networks whose destination element is ``t`` (hermnet.py:60-61); None: none is active."""
+            x_acc = v_acc = None
+            # unbind / split instead of indexing: their backward builds ONE gradient buffer, a slice per sub-network
+            # would allocate a full-size zero tensor each
+            dxs, dvs = dxt.unbind(1), dvt.unbind(1)
+            for m, slots in self._dst_modules(t):
+                mod = mods[m]
+                if self.KIND == "HTNet":
+                    pa = dvs[slots[0]]
+                    pc = dvs[slots[1]] if slots[1] != slots[0] else pa
+                    dxm = dxs[slots[0]] + (dxs[slots[1]] if slots[1] != slots[0] else 0)
+                    dvm = pa + pc if slots[1] != slots[0] else pa
+                    na = torch.sqrt((pa ** 2).sum(dim=1) + 1e-8)
+                    nc = torch.sqrt((pc ** 2).sum(dim=1) + 1e-8)
+                    vdot = (pa * pc).sum(dim=1) / (na * nc)
+                else:
+                    dxm, dvm, vdot = dxs[slots[0]], dvs[slots[0]], None
+                if not g.mod_active_host[m]:                         # hermnet.py:56-57: no edges -> rows stay 0
+                    continue
+                v_new, x_new = mod.node_update(xt, vt, dxm, dvm, vdot, lin)
+                x_acc = x_new if x_acc is None else x_acc + x_new
+                v_acc = v_new if v_acc is None else v_acc + v_new
+            return x_acc, v_acc
+
+        sizes = []
+        for t in range(T):
+            sl = g.dst_slice(t)
+            sizes += [sl.stop - sl.start, g.type_ptr[t + 1] - sl.stop]      # owned rows, ghost rows of element t
+        sizes.append(g.type_ptr[T + 1] - g.type_ptr[T])                    # atoms of unknown elements
+        x_p, vec_p, dx_p, dvec_p = (torch.split(a, sizes, dim=0) for a in (x, vec, dx, dvec))
         for t in range(T):
             sl = g.dst_slice(t)
             n_ghost_t = g.type_ptr[t + 1] - sl.stop
             if sl.stop > sl.start:
-                xt, vt = x[sl], vec[sl]
-                x_acc = v_acc = None
-                for m, slots in self._dst_modules(t):
-                    mod = mods[m]
-                    if self.KIND == "HTNet":
-                        pa = dvec[sl, slots[0]]
-                        pc = dvec[sl, slots[1]] if slots[1] != slots[0] else pa
-                        dxm = dx[sl, slots[0]] + (dx[sl, slots[1]] if slots[1] != slots[0] else 0)
-                        dvm = pa + pc if slots[1] != slots[0] else pa
-                        na = torch.sqrt((pa ** 2).sum(dim=1) + 1e-8)
-                        nc = torch.sqrt((pc ** 2).sum(dim=1) + 1e-8)
-                        vdot = (pa * pc).sum(dim=1) / (na * nc)
-                    else:
-                        dxm, dvm, vdot = dx[sl, slots[0]], dvec[sl, slots[0]], None
-                    if not g.mod_active_host[m]:                         # hermnet.py:56-57: no edges -> rows stay 0
-                        continue
-                    v_new, x_new = mod.node_update(xt, vt, dxm, dvm, vdot, lin)
-                    x_acc = x_new if x_acc is None else x_acc + x_new
-                    v_acc = v_new if v_acc is None else v_acc + v_new
-                if x_acc is None:
-                    pad(sl.stop - sl.start)
-                else:
+                if any(g.mod_active_host[m] for m, _ in self._dst_modules(t)):
+                    args = (t, x_p[2 * t], vec_p[2 * t], dx_p[2 * t], dvec_p[2 * t])
+                    # memory-bound configurations: keep one element's update intermediates at a time
+                    x_acc, v_acc = (torch_checkpoint(update_type, *args, use_reentrant=False)
+                                    if ckpt and torch.is_grad_enabled() else update_type(*args))
                     xs.append(x_acc)
                     vs.append(v_acc)
+                else:
+                    pad(sl.stop - sl.start)
             if n_ghost_t:
                 pad(n_ghost_t)                                           # ghost rows: refreshed by the halo exchange
         n_unknown = g.type_ptr[T + 1] - g.type_ptr[T]
         if n_unknown:
             pad(n_unknown)
         return torch.cat(xs, 0), torch.cat(vs, 0)
+
+    def _want_checkpoint(self, g: RowGraph, pos) -> bool:
+        """Edge-side tensors a layer keeps for its backward pass: xh (+ its gradient), dx / dvec (+ gradients) and the
+        update block's intermediates -- about 3 x (xh rows x 3F + rows x 4F) floats.  Recompute instead of keeping them when
+        all layers together would take more than half of the device memory (HTNet with many elements: 30 rows per atom)."""
+        if not pos.is_cuda:
+            return False
+        F = self.hidden_channels
+        per_layer = 3.0 * 4.0 * (float(g.xh_base[-1]) * 3 * F + float(g.n_rows) * 4 * F)
+        total = torch.cuda.get_device_properties(pos.device).total_memory
+        return per_layer * self.num_layers > 0.5 * total
 
     @staticmethod
     def _layer0_tables(g: RowGraph, z0):

@@ -141,3 +141,25 @@ def test_cpu_input_without_emulator_fails_loudly():
     model = H.HVNet(["H", "O"], num_layers=1, hidden_channels=32, num_rbf=16)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         model(H.Data(pos=torch.zeros(3, 3), atomic_number=torch.ones(3, dtype=torch.long)))
+
+
+def test_layer_checkpointing_gives_identical_energy_and_forces(emu):
+    """checkpoint_layers=True recomputes every layer in the backward pass (memory of one layer instead of all:
+    BASELINE config 5, HTNet with 30 rows per atom) -- results must be bit-identical to the stored-activation path."""
+    from tests.util import lattice_system
+    pos, Z, cell = lattice_system(3, [1, 8], 5)
+    for kind in ("HVNet", "HTNet"):
+        torch.manual_seed(0)
+        model = getattr(H, kind)(elems=["H", "O"], rc=5.0, num_layers=2, hidden_channels=32, num_rbf=16).eval()
+        for p in model.parameters():
+            p.requires_grad_(False)
+        out = []
+        for ck in (False, True):
+            model.checkpoint_layers = ck
+            d = H.Data(pos=pos.clone().requires_grad_(True), atomic_number=Z, cell=cell.clone().requires_grad_(True))
+            e = model(d)
+            gp, gc = torch.autograd.grad(e.sum(), [d.pos, d.cell])
+            out.append((e.detach(), gp, gc))
+        assert all(torch.equal(a, b) for a, b in zip(*out))
+        model.checkpoint_layers = None
+        assert model._want_checkpoint(model.build_graph(pos, Z, cell), pos) is False      # CPU tensors: never
