@@ -145,3 +145,19 @@ def test_null_vec_equals_zero_vec(variant, F, K):
     _close(dx1, dx0, "dx", 1e-6)
     _close(dv1, dv0, "dvec", 1e-6)
     _close(gg1, gg0, "g_geom", 1e-6)
+
+
+@pytest.mark.parametrize("F,K,exponent", [(64, 200, 3), (128, 256, 7), (128, 12, 5)])
+def test_other_envelope_exponents_and_basis_sizes(F, K, exponent):
+    """Polynomial envelope with p != 5 (rmnet.py:183-193 is generic in p), K > 128 and K at the band width."""
+    import hermnet_b200 as H
+    dev = "cuda:0"
+    pos, Z, cell = _system(6, [1, 8], 11)
+    pos, Z, cell = pos.to(dev), Z.to(dev), cell.to(dev)
+    torch.manual_seed(5)
+    model = H.HVNet(elems=["H", "O"], rc=5.0, num_layers=2, hidden_channels=F, num_rbf=K,
+                    envelope={"name": "polynomial", "exponent": exponent}).to(dev).eval()
+    for p in model.parameters():
+        p.requires_grad_(False)
+    g = model.build_graph(pos, Z, cell)
+    _compare(model, g, pos, cell)
