@@ -84,12 +84,13 @@ __device__ __forceinline__ float dssilu(float z) {
 
 template <int BN>
 struct Smem {
-    static constexpr int kStages = BN == 128 ? 2 : 3;
+    // three operand stages in flight (with two, the tensor pipe sat at 36 %: every K-chunk waited a full TMA round trip)
+    static constexpr int kStages = 3;
     static constexpr int kA = BM * BK * 4;   // 16 KB
     static constexpr int kB = BN * BK * 4;
     static constexpr int kStage = 2 * kA + 2 * kB;
-    static constexpr int kStaging = kStages * kStage;          // 4 x 16 KB: (C, C2) x double buffer
-    static constexpr int kBars = kStaging + 4 * 16384;
+    static constexpr int kStaging = kStages * kStage;          // 2 x 16 KB: C double-buffered, or (C, C2) single-buffered
+    static constexpr int kBars = kStaging + 2 * 16384;
     static constexpr int kTotal = kBars + 256 + 1024;   // barriers + tmem slot, + slack for 1024-byte alignment
 };
 
@@ -252,9 +253,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     asm volatile("bar.sync 2, 128;" ::: "memory");
                     if (t == 0) mbar_arrive(tempty0 + 8 * a);
                 }
-                uint8_t *sC = stg + buf * 16384, *sC2 = stg + (2 + buf) * 16384;
-                // the TMA store that last read this buffer (two chunks ago) must have finished reading it
-                if (t == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(1) : "memory");
+                // one output: the two 16 KB staging buffers alternate (the TMA store that read this one two chunks ago must be
+                // done reading); two outputs (mode 1 with C2): one buffer each, the previous chunk's stores must be done
+                uint8_t *sC = two ? stg : stg + buf * 16384, *sC2 = stg + 16384;
+                if (t == 0) {
+                    if (two) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(0) : "memory");
+                    else asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(1) : "memory");
+                }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
