@@ -161,3 +161,20 @@ def test_other_envelope_exponents_and_basis_sizes(F, K, exponent):
         p.requires_grad_(False)
     g = model.build_graph(pos, Z, cell)
     _compare(model, g, pos, cell)
+
+
+@pytest.mark.parametrize("name", ["triclinic_multi_image", "cluster_nonpbc_capped", "batch3_mixed"])
+@pytest.mark.parametrize("F", [64, 128])
+def test_sweep_kernels_on_the_golden_geometries(name, F):
+    """The golden systems' geometries (5-atom triclinic cell with rc > L/2: several images of the same pair, self edges;
+    a capped non-periodic cluster; a mixed batch) through the sweep kernels, against the row kernels and float64."""
+    from tests import util
+    case = util.load_case(name)
+    dev = "cuda:0"
+    elems = case["cfg"]["elems"]
+    model = _model("HVNet", elems, F, 24, dev)
+    pos, Z = case["pos"].to(dev), case["Z"].to(dev)
+    cell = None if case["cell"] is None else case["cell"].to(dev)
+    batch = case["batch"].to(dev)
+    g = model.builder.from_positions(pos, Z, cell, batch)
+    _compare(model, g, pos, cell)
