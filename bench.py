@@ -42,7 +42,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C4")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the box edge (debug only; 1.0 = BASELINE size)")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -282,7 +282,8 @@ def main():
     # ---- end to end from host buffers ------------------------------------------------------------------------
     e2e_s = float("nan")
     if args.e2e_steps > 0:
-        step_e2e()
+        for _ in range(2):      # warm-up: the caching allocator settles on the block sizes of a freshly built graph
+            step_e2e()
         barrier()
         w0 = time.perf_counter()
         for _ in range(args.e2e_steps):

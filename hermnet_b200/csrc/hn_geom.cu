@@ -210,12 +210,18 @@ extern "C" int hn_segment_sum(const float *Y, const int32_t *rowptr, const int32
         const int total = n_rows * C;
         int chunks = (sms * 4 + total - 1) / total;
         chunks = chunks < 1 ? 1 : (chunks > 256 ? 256 : chunks);
-        double *partial = nullptr;    // stream-ordered scratch: no library-owned state
-        HN_CUDA(cudaMallocAsync((void **)&partial, sizeof(double) * (size_t)total * chunks, (cudaStream_t)stream), "hn_segment_sum");
+        // chunk partials: a per-device scratch buffer of the library (8 MB, allocated on first use, never freed; calls
+        // on one device are expected to come from one stream at a time).  cudaMallocAsync here made every synchronised
+        // step re-grow the driver's pool (100+ ms stalls next to torch's caching allocator).
+        static double *scratch[64] = {nullptr};
+        int dev = 0;
+        HN_CUDA(cudaGetDevice(&dev), "hn_segment_sum");
+        HN_REQUIRE(dev >= 0 && dev < 64, "hn_segment_sum", "device ordinal out of range");
+        if (scratch[dev] == nullptr) HN_CUDA(cudaMalloc((void **)&scratch[dev], sizeof(double) * 4096 * 256), "hn_segment_sum");
+        double *partial = scratch[dev];
         dim3 grid(n_rows, C, chunks);
         segment_sum_long_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(Y, rowptr, perm, C, chunks, partial);
         segment_sum_finish_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partial, total, chunks, out);
-        HN_CUDA(cudaFreeAsync(partial, (cudaStream_t)stream), "hn_segment_sum");
     } else {
         const long long total = (long long)n_rows * C;
         long long blocks = (total + 255) / 256;

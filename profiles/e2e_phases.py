@@ -22,7 +22,9 @@ def tick():
     return time.perf_counter()
 
 
-for it in range(4):
+import gc
+n_it = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+for it in range(n_it):
     t0 = tick()
     p_, z_, c_ = pos_h.to(dev, non_blocking=True), Z_h.to(dev, non_blocking=True), cell_h.to(dev, non_blocking=True)
     t1 = tick()
@@ -41,4 +43,5 @@ for it in range(4):
     (g2,) = torch.autograd.grad(e2.sum(), d.pos)
     t7 = tick()
     print(f"{name} it{it}: h2d {1e3*(t1-t0):.2f}  build_graph {1e3*(t2-t1):.2f}  forward_graph {1e3*(t3-t2):.2f}  backward {1e3*(t4-t3):.2f}  "
-          f"d2h {1e3*(t5-t4):.2f} | model(data) {1e3*(t6-t5):.2f}  backward {1e3*(t7-t6):.2f} ms", flush=True)
+          f"d2h {1e3*(t5-t4):.2f} | model(data) {1e3*(t6-t5):.2f}  backward {1e3*(t7-t6):.2f} ms | alloc {torch.cuda.memory_allocated()/2**30:.1f} GiB "
+          f"reserved {torch.cuda.memory_reserved()/2**30:.1f} GiB gc {gc.get_count()}", flush=True)
