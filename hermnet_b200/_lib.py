@@ -21,6 +21,13 @@ class EdgeParams(Structure):
 
 P = c_void_p  # every device pointer crosses the ABI as a plain address
 
+
+class TcPlan(Structure):
+    """``hn_tc_plan``: tile plan of the tensor-core edge kernels (device pointers)."""
+    _fields_ = [("n_blocks", c_int32), ("n_tiles", c_int32), ("blk_info", c_void_p), ("blk_tile", c_void_p),
+                ("tile_info", c_void_p), ("tile_win", c_void_p), ("erec", c_void_p)]
+
+
 # name -> (restype, argtypes); must list EVERY symbol of include/hermnet_b200.h (checked by tests/test_abi.py)
 SIGNATURES = {
     "hn_abi_version": (c_int32, []),
@@ -43,6 +50,19 @@ SIGNATURES = {
     "hn_painn_edge_bwd_dst": (c_int32, [POINTER(EdgeParams)] + [P] * 13 + [c_int64, P]),
     "hn_painn_edge_bwd_src": (c_int32, [POINTER(EdgeParams)] + [P] * 16),
     "hn_painn_edge_bwd_w": (c_int32, [POINTER(EdgeParams)] + [P] * 12 + [c_int32, P]),
+    "hn_tc_supported": (c_int32, [c_int32, c_int32]),
+    "hn_tc_block_rows": (c_int32, []),
+    "hn_tc_tile_edges": (c_int32, []),
+    "hn_tc_split_weights_elems": (c_int64, [c_int32, c_int32, c_int32]),
+    "hn_tc_split_weights": (c_int32, [P, c_int32, c_int32, c_int32, P, P, P]),
+    "hn_tc_basis_index": (c_int32, [P, c_int64, c_float, c_int32, P, P]),
+    "hn_tc_plan_count": (c_int32, [P, P, P, c_int32, c_int32, P, P]),
+    "hn_tc_plan_fill": (c_int32, [P, P, P, c_int32, c_int32, P, P, P]),
+    "hn_tc_plan_finalize": (c_int32, [P, P, c_int32, c_int64, P, P, P, P, P]),
+    "hn_tc_tile_windows": (c_int32, [POINTER(TcPlan), P, c_float, c_int32, P]),
+    "hn_tc_edge_fwd": (c_int32, [POINTER(EdgeParams), POINTER(TcPlan)] + [P] * 10 + [c_int64, P]),
+    "hn_tc_edge_bwd_dst": (c_int32, [POINTER(EdgeParams), POINTER(TcPlan)] + [P] * 11),
+    "hn_tc_edge_bwd_src": (c_int32, [POINTER(EdgeParams), POINTER(TcPlan)] + [P] * 12),
     "hn_gemm_tf32x3": (c_int32, [P, c_int64, c_int64, c_int64, P, P, c_int64, P, P, c_int64, P]),
     "hn_gemm_tf32x3_ex": (c_int32, [P, c_int64, c_int64, c_int64, P, P, c_int64, P, P, c_int64, c_int32, P, c_int64, P, c_int64, P]),
     "hn_node_pre": (c_int32, [c_int64, c_int32, P, P, c_int64, P, P, c_int64, P, P, P]),

@@ -20,7 +20,7 @@ import torch
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
-from . import ops
+from . import ops, tileplan
 from .graph import RowGraph, Segments
 
 Tensor = torch.Tensor
@@ -95,8 +95,9 @@ def edge_geometry(pos: Tensor, cell: Optional[Tensor], g: RowGraph) -> Tensor:
 
 
 class _PaiNNEdge(Function):
-    """Edge side of one layer: the C ABI picks the tile-sweep kernels (F in {64, 128, 256, 512}) or the row-per-warp
-    kernels (any F % 32 == 0)."""
+    """Edge side of one layer.  F == 128: the tensor-core kernels of csrc/hn_edge_tc.cu over the graph's tile plans
+    (``tileplan``); otherwise the C ABI picks the tile-sweep kernels (F in {64, 256, 512}) or the row-per-warp kernels
+    (any F % 32 == 0)."""
 
     @staticmethod
     def forward(ctx, xh, vec, geom, Wt, bias, offset, g: RowGraph, p, vec_zero=False):
@@ -104,7 +105,15 @@ class _PaiNNEdge(Function):
         # vec == 0 identically (first layer, hermnet.py:124): the kernels take NULL and skip the vec gathers and the F:2F
         # part of the filter in the forward and the destination-major backward
         ctx.vec_null = bool(vec_zero)
-        dx, dvec = ops.painn_edge_fwd(p, xh, None if ctx.vec_null else vec, geom, g, Wt, bias, offset)
+        ctx.tc = ops.edge_use_tc(p.hidden, p.num_rbf) and g.n_edges > 0
+        if ctx.tc:
+            dst, _ = tileplan.plans_of(g, geom, p.inv_rc, p.num_rbf, want_src=False)
+            dst.update_windows(geom, p.inv_rc, p.num_rbf)
+            wsplit, wscale = ops.tc_split_weights(Wt)
+            dx, dvec = ops.tc_edge_fwd(p, dst, xh, None if ctx.vec_null else vec, geom, wsplit, wscale, bias, offset, p.n_rows)
+            ctx.wsplit = (wsplit, wscale)
+        else:
+            dx, dvec = ops.painn_edge_fwd(p, xh, None if ctx.vec_null else vec, geom, g, Wt, bias, offset)
         ctx.g, ctx.p = g, p
         ctx.save_for_backward(xh, vec, geom, Wt, bias, offset)
         return dx, dvec
@@ -117,11 +126,23 @@ class _PaiNNEdge(Function):
         g_dx, g_dvec = g_dx.contiguous(), g_dvec.contiguous()
         need = ctx.needs_input_grad
         grad_xh = grad_vec = grad_geom = grad_W = grad_b = None
+        tc_src = ctx.tc and getattr(g, "_tc_parent", None) is None      # the element-table graph has no source-major plan
+        if ctx.tc:
+            wsplit, wscale = ctx.wsplit
+            dst, src = tileplan.plans_of(g, geom, p.inv_rc, p.num_rbf, want_src=tc_src and (need[0] or need[1]))
         if need[2]:
-            parts = ops.painn_edge_bwd_dst(p, xh, None if ctx.vec_null else vec, geom, g, Wt, bias, offset, g_dx, g_dvec)
+            if ctx.tc:
+                dst.update_windows(geom, p.inv_rc, p.num_rbf)
+                parts = ops.tc_edge_bwd_dst(p, dst, xh, None if ctx.vec_null else vec, geom, wsplit, wscale, bias, offset, g_dx, g_dvec)
+            else:
+                parts = ops.painn_edge_bwd_dst(p, xh, None if ctx.vec_null else vec, geom, g, Wt, bias, offset, g_dx, g_dvec)
             grad_geom = parts[0] if parts.size(0) == 1 else parts.sum(0)
         if need[0] or need[1]:
-            grad_xh, grad_vec = ops.painn_edge_bwd_src(p, xh, vec, geom, g, Wt, bias, offset, g_dx, g_dvec)
+            if tc_src:
+                src.update_windows(geom, p.inv_rc, p.num_rbf)
+                grad_xh, grad_vec = ops.tc_edge_bwd_src(p, src, xh, vec, geom, wsplit, wscale, bias, offset, g_dx, g_dvec)
+            else:
+                grad_xh, grad_vec = ops.painn_edge_bwd_src(p, xh, vec, geom, g, Wt, bias, offset, g_dx, g_dvec)
         if need[3] or need[4]:
             grad_W, grad_b = ops.painn_edge_bwd_w(p, xh, vec, geom, g, offset, g_dx, g_dvec)
         return grad_xh, grad_vec, grad_geom, grad_W, grad_b, None, None, None, None

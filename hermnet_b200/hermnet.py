@@ -16,6 +16,7 @@ What changed underneath (hermnet.py:37-65,118-152 + utils.py:11-24 + rmnet.py:51
 from __future__ import annotations
 
 import copy
+import weakref
 
 from typing import Dict, List, Optional, Union
 
@@ -163,7 +164,8 @@ class _HermNet(nn.Module):
         e_atom = self.out_energy[2](h)                                   # [N,1]   hermnet.py:129
         sb = g.seg_batch
         energy = Fn.segment_sum(e_atom, sb).squeeze(1)[: g.n_graphs]     # hermnet.py:130 (owned atoms only)
-        if self.intensive:
+        if self.intensive and halo is None:
+            # (domain decomposition: a rank only holds a partial sum -- DomainDecomposition divides by the GLOBAL count)
             energy = energy / (sb.rowptr[1:] - sb.rowptr[:-1])[: g.n_graphs].clamp(min=1).to(energy.dtype)
         return energy, x, vec
 
@@ -179,16 +181,16 @@ class _HermNet(nn.Module):
             # frozen HVNet parameters on the fused path: hand-written forward/backward for the whole node side
             Wt = torch.stack([m.message_layer.rbf_proj.weight.t() for m in mods])
             bias = torch.stack([m.message_layer.rbf_proj.bias for m in mods])
-            if vec_zero and z0 is not None:
+            if vec_zero and z0 is not None and not self.embed.weight.requires_grad:
                 # first layer: x = Embedding[Z] (hermnet.py:123), so the projected source features only depend on the
                 # ELEMENT of the source.  The edge kernels read a [M * n_elements, 3F] table (L1-resident) through an
                 # element-index copy of the column array instead of gathering N distinct rows, and the x_proj GEMMs
                 # shrink from N rows to n_elements rows.  Same arithmetic per row as rmnet.py:52.
-                uniq, col0, xoff0 = self._layer0_tables(g, z0)
+                # (only while the embedding is frozen: the kernels' source-major backward is indexed by source ATOM, a
+                # trainable embedding takes the general path below)
+                uniq, g0 = self._layer0_tables(g, z0)
                 xs = self.embed(uniq)
                 xh = torch.cat([m.message_layer.node_features(xs) for m in mods], 0)
-                g0 = copy.copy(g)
-                g0.col, g0.row_xoff, g0._lazy = col0, xoff0, {}
                 p0 = ops.EdgeParams(int(uniq.numel()), p.n_rows, p.n_modules, p.hidden, p.num_rbf, p.env_p, p.inv_rc, p.coeff)
                 dx, dvec = Fn.painn_edge(xh, vec, geom, Wt, bias, self.radial_basis.rbf.offset, g0, p0, True)
             else:
@@ -300,14 +302,18 @@ class _HermNet(nn.Module):
 
     @staticmethod
     def _layer0_tables(g: RowGraph, z0):
-        """(distinct atomic numbers, element index of every row-edge's source, xh row offset of every row) for the
-        first-layer element table; cached on the graph (the species of a graph never change)."""
+        """(distinct atomic numbers, view ``g0`` of the graph for the first-layer element table: ``col`` = element index
+        of every row-edge's source, ``row_xoff`` = table offset of every row); cached on the graph (the species of a
+        graph never change)."""
         hit = g._lazy.get("layer0")
         if hit is None:
             uniq, inv = torch.unique(z0, return_inverse=True)
-            col0 = inv.to(torch.int32)[g.col.long()].contiguous()
-            xoff0 = (g.row_mod.long().clamp(min=0) * int(uniq.numel())).contiguous()
-            hit = g._lazy["layer0"] = (uniq, col0, xoff0)
+            g0 = copy.copy(g)
+            g0.col = inv.to(torch.int32)[g.col.long()].contiguous()
+            g0.row_xoff = (g.row_mod.long().clamp(min=0) * int(uniq.numel())).contiguous()
+            g0._lazy = {}
+            g0._tc_parent = weakref.ref(g)      # (weak: g._lazy owns g0)
+            hit = g._lazy["layer0"] = (uniq, g0)
         return hit
 
     def _fused_node_path(self, conv, p, g: RowGraph) -> bool:

@@ -242,9 +242,24 @@ def edge_num_slices(hidden: int) -> int:
     return n
 
 
+import os as _os
+
+# 'auto': tensor-core kernels (hn_edge_tc.cu) where supported (F == 128), else the tile-sweep kernels (F % 64 == 0), else
+# the row-per-warp kernels; 'quad' / 'row' pin the older families (A/B measurements, tests).  HERMNET_B200_EDGE presets it.
+EDGE_VARIANT = {"v": _os.environ.get("HERMNET_B200_EDGE", "auto") if _os.environ.get("HERMNET_B200_EDGE", "auto") in
+                ("auto", "tc", "quad", "row") else "auto"}
+
+
 def edge_set_variant(variant: str) -> None:
-    """'auto': quad-tile edge kernels where supported (F % 64 == 0), 'row': row-per-warp kernels only (A/B measurements)."""
-    _lib.check(_lib.load().hn_painn_edge_set_variant({"auto": 0, "row": 1}[variant]), "hn_painn_edge_set_variant")
+    """'auto' / 'tc': tensor-core edge kernels where supported; 'quad': tile-sweep kernels; 'row': row-per-warp kernels."""
+    if variant not in ("auto", "tc", "quad", "row"):
+        raise ValueError(variant)
+    EDGE_VARIANT["v"] = variant
+    _lib.check(_lib.load().hn_painn_edge_set_variant(1 if variant == "row" else 0), "hn_painn_edge_set_variant")
+
+
+def edge_use_tc(hidden: int, num_rbf: int) -> bool:
+    return EDGE_VARIANT["v"] in ("auto", "tc") and tc_supported(hidden, num_rbf)
 
 
 def painn_edge_fwd(p: EdgeParams, xh, vec, geom, g, Wt, bias, offset):
@@ -452,3 +467,122 @@ def node_pre_bwd(g_xn, g_cat, g_vecn, g_vecp, g_x, g_vec):
     with torch.cuda.device(dev), _timed("node_elementwise", dev):
         _lib.check(lib.hn_node_pre_bwd(n, F, _ptr(g_xn), _ptr(g_cat), _ptr(g_vecn), _ptr(g_vecp), _ptr(g_x), _ptr(g_vec),
                                        _stream(dev)), "hn_node_pre_bwd")
+
+
+# ----------------------------------------------------------------------------------------------------
+# tensor-core edge kernels (csrc/hn_edge_tc.cu): tile plan, weight split, forward / backward
+# ----------------------------------------------------------------------------------------------------
+def tc_supported(hidden: int, num_rbf: int) -> bool:
+    return bool(_lib.load().hn_tc_supported(int(hidden), int(num_rbf)))
+
+
+def tc_block_rows() -> int:
+    return int(_lib.load().hn_tc_block_rows())
+
+
+def tc_split_weights(Wt: Tensor):
+    """``Wt [M,K,3F]`` -> fp16 (hi | lo) rows ``[M*3F, 2, K32]`` scaled by a per-module power of two, ``wscale [M]``."""
+    lib = _lib.load()
+    dev = _chk("tc_split_weights", Wt)
+    _f32("tc_split_weights", Wt)
+    M, K, F3 = Wt.shape
+    n = int(lib.hn_tc_split_weights_elems(M, F3 // 3, K))
+    wsplit = torch.empty(n, dtype=torch.float16, device=dev)
+    wscale = torch.empty(M, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev), _timed("tc_split_weights", dev):
+        _lib.check(lib.hn_tc_split_weights(_ptr(Wt), M, K, F3 // 3, _ptr(wsplit), _ptr(wscale), _stream(dev)), "hn_tc_split_weights")
+    return wsplit, wscale
+
+
+def tc_basis_index(geom: Tensor, inv_rc: float, num_rbf: int) -> Tensor:
+    lib = _lib.load()
+    dev = _chk("tc_basis_index", geom)
+    kc = torch.empty(geom.size(0), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev), _timed("tc_plan", dev):
+        _lib.check(lib.hn_tc_basis_index(_ptr(geom), geom.size(0), float(inv_rc), int(num_rbf), _ptr(kc), _stream(dev)),
+                   "hn_tc_basis_index")
+    return kc
+
+
+def tc_plan_count(order: Tensor, kc: Tensor, grp_ptr: Tensor, n_groups: int, num_rbf: int) -> Tensor:
+    lib = _lib.load()
+    dev = _chk("tc_plan_count", order, kc, grp_ptr)
+    _i32("tc_plan_count", order, kc, grp_ptr)
+    counts = torch.zeros(n_groups, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev), _timed("tc_plan", dev):
+        _lib.check(lib.hn_tc_plan_count(_ptr(order), _ptr(kc), _ptr(grp_ptr), n_groups, int(num_rbf), _ptr(counts), _stream(dev)),
+                   "hn_tc_plan_count")
+    return counts
+
+
+def tc_plan_fill(order: Tensor, kc: Tensor, grp_ptr: Tensor, n_groups: int, num_rbf: int, grp_tile: Tensor, n_tiles: int) -> Tensor:
+    lib = _lib.load()
+    dev = _chk("tc_plan_fill", order, kc, grp_ptr, grp_tile)
+    _i32("tc_plan_fill", order, kc, grp_ptr, grp_tile)
+    tile_start = torch.empty(max(n_tiles, 1), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev), _timed("tc_plan", dev):
+        _lib.check(lib.hn_tc_plan_fill(_ptr(order), _ptr(kc), _ptr(grp_ptr), n_groups, int(num_rbf), _ptr(grp_tile), _ptr(tile_start),
+                                       _stream(dev)), "hn_tc_plan_fill")
+    return tile_start
+
+
+def tc_plan_finalize(order: Tensor, tile_start: Tensor, n_tiles: int, n_edges: int, rec: Tensor, tile_mod: Tensor):
+    lib = _lib.load()
+    dev = _chk("tc_plan_finalize", order, tile_start, rec, tile_mod)
+    _i32("tc_plan_finalize", order, tile_start, rec, tile_mod)
+    erec = torch.empty((max(n_edges, 1), 4), dtype=torch.int32, device=dev)
+    tile_info = torch.empty((max(n_tiles, 1), 4), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev), _timed("tc_plan", dev):
+        _lib.check(lib.hn_tc_plan_finalize(_ptr(order), _ptr(tile_start), n_tiles, n_edges, _ptr(rec), _ptr(tile_mod), _ptr(erec),
+                                           _ptr(tile_info), _stream(dev)), "hn_tc_plan_finalize")
+    return erec, tile_info
+
+
+def tc_tile_windows(plan, geom: Tensor, inv_rc: float, num_rbf: int) -> None:
+    lib = _lib.load()
+    dev = _chk("tc_tile_windows", geom)
+    with torch.cuda.device(dev), _timed("tc_tile_windows", dev):
+        _lib.check(lib.hn_tc_tile_windows(ctypes.byref(plan.cstruct()), _ptr(geom), float(inv_rc), int(num_rbf), _stream(dev)),
+                   "hn_tc_tile_windows")
+
+
+def tc_edge_fwd(p: EdgeParams, plan, xh, vec, geom, wsplit, wscale, bias, offset, n_rows: int, debug_phi: bool = False):
+    lib = _lib.load()
+    dev = _chk("tc_edge_fwd", xh, vec, geom, wsplit, wscale, bias, offset)
+    _f32("tc_edge_fwd", xh, vec, geom, wscale, bias, offset)
+    F = p.hidden
+    dx = torch.empty((n_rows, F), dtype=torch.float32, device=dev)
+    dvec = torch.empty((n_rows, 3, F), dtype=torch.float32, device=dev)
+    E = geom.size(0)
+    dbg = torch.zeros(2 * E * 3 * F + 14336, dtype=torch.float32, device=dev) if debug_phi else None
+    with torch.cuda.device(dev), _timed("painn_edge_fwd", dev):
+        _lib.check(lib.hn_tc_edge_fwd(ctypes.byref(p), ctypes.byref(plan.cstruct()), _ptr(xh), _ptr(vec), _ptr(geom), _ptr(wsplit),
+                                      _ptr(wscale), _ptr(bias), _ptr(offset), _ptr(dx), _ptr(dvec), _ptr(dbg), E, _stream(dev)),
+                   "hn_tc_edge_fwd")
+    return (dx, dvec, dbg) if debug_phi else (dx, dvec)
+
+
+def tc_edge_bwd_dst(p: EdgeParams, plan, xh, vec, geom, wsplit, wscale, bias, offset, g_dx, g_dvec):
+    lib = _lib.load()
+    dev = _chk("tc_edge_bwd_dst", xh, vec, geom, wsplit, wscale, bias, offset, g_dx, g_dvec)
+    _f32("tc_edge_bwd_dst", xh, vec, geom, wscale, bias, offset, g_dx, g_dvec)
+    alloc = torch.zeros if plan.has_inactive else torch.empty
+    g_geom = alloc((1, geom.size(0), 4), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev), _timed("painn_edge_bwd_dst", dev):
+        _lib.check(lib.hn_tc_edge_bwd_dst(ctypes.byref(p), ctypes.byref(plan.cstruct()), _ptr(xh), _ptr(vec), _ptr(geom), _ptr(wsplit),
+                                          _ptr(wscale), _ptr(bias), _ptr(offset), _ptr(g_dx), _ptr(g_dvec), _ptr(g_geom),
+                                          _stream(dev)), "hn_tc_edge_bwd_dst")
+    return g_geom
+
+
+def tc_edge_bwd_src(p: EdgeParams, plan, xh, vec, geom, wsplit, wscale, bias, offset, g_dx, g_dvec):
+    lib = _lib.load()
+    dev = _chk("tc_edge_bwd_src", xh, vec, geom, wsplit, wscale, bias, offset, g_dx, g_dvec)
+    _f32("tc_edge_bwd_src", xh, vec, geom, wscale, bias, offset, g_dx, g_dvec)
+    grad_xh = torch.zeros_like(xh)
+    grad_vec = torch.empty_like(vec)
+    with torch.cuda.device(dev), _timed("painn_edge_bwd_src", dev):
+        _lib.check(lib.hn_tc_edge_bwd_src(ctypes.byref(p), ctypes.byref(plan.cstruct()), _ptr(xh), _ptr(vec), _ptr(geom), _ptr(wsplit),
+                                          _ptr(wscale), _ptr(bias), _ptr(offset), _ptr(g_dx), _ptr(g_dvec), _ptr(grad_xh),
+                                          _ptr(grad_vec), _stream(dev)), "hn_tc_edge_bwd_src")
+    return grad_xh, grad_vec

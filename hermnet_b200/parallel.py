@@ -204,6 +204,8 @@ class DomainDecomposition:
         """Total energy ``[1]`` and ``dE/dpos [N,3]`` (forces = minus that), identical on every rank."""
         p = pos.detach()[self.ids].requires_grad_(True)
         e, _, _ = self.model.forward_graph(p, self.Z_local, self.cell, self.graph, halo=self.halo)
+        if getattr(self.model, "intensive", False):       # mean over ALL atoms of the system (hermnet.py:130), not per rank
+            e = e / float(max(self.n_atoms, 1))
         (gl,) = torch.autograd.grad(e.sum(), p)
         grad = torch.zeros((self.n_atoms, 3), dtype=gl.dtype, device=gl.device)
         grad.index_add_(0, self.ids, gl)                               # ids are unique per rank: no collisions

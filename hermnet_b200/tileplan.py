@@ -1,0 +1,174 @@
+"""Tile plans of the tensor-core edge kernels (``csrc/hn_edge_tc.cu``).
+
+A plan regroups the row-edges of a ``RowGraph`` once per configuration -- what the reference redoes per layer and per
+element with ``in_subgraph`` (HermNet/utils.py:11-24) -- into *blocks* (32 rows of one sub-network, or 32 consecutive
+source atoms) and *tiles* (<= 64 edges of a block whose Gaussian bands fit one 32-wide window of the basis index), so
+that the filter projection of a tile (rmnet.py:45,55) is ONE tensor-core tile  W[3F x 32] . basis[32 x 64].
+
+``dst`` plans drive the forward and the destination-major backward, ``src`` plans the source-major backward.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import ops
+from ._lib import TcPlan
+
+Tensor = torch.Tensor
+
+
+class TilePlan:
+    def __init__(self, kind: str, blk_info, blk_tile, tile_info, erec, n_blocks: int, n_tiles: int, has_inactive: bool):
+        self.kind = kind
+        self.blk_info, self.blk_tile, self.tile_info, self.erec = blk_info, blk_tile, tile_info, erec
+        self.n_blocks, self.n_tiles, self.has_inactive = n_blocks, n_tiles, has_inactive
+        self.tile_win = torch.zeros((max(n_tiles, 1), 2), dtype=torch.int32, device=erec.device)
+        self.win_key = None        # (data_ptr, version) of the geometry the windows were computed for
+        self._c = None
+
+    def cstruct(self) -> TcPlan:
+        if self._c is None:
+            self._c = TcPlan(self.n_blocks, self.n_tiles, self.blk_info.data_ptr(), self.blk_tile.data_ptr(),
+                             self.tile_info.data_ptr(), self.tile_win.data_ptr(), self.erec.data_ptr())
+        return self._c
+
+    def with_erec(self, erec: Tensor) -> "TilePlan":
+        """Same tiling, different edge records (first-layer element table)."""
+        q = TilePlan(self.kind, self.blk_info, self.blk_tile, self.tile_info, erec, self.n_blocks, self.n_tiles, self.has_inactive)
+        q.tile_win = self.tile_win          # shared: the windows only depend on the geometry
+        q._shared_with = self
+        return q
+
+    def update_windows(self, geom: Tensor, inv_rc: float, num_rbf: int) -> None:
+        owner = getattr(self, "_shared_with", self)
+        key = (geom.data_ptr(), geom._version, tuple(geom.shape))
+        if owner.win_key != key:
+            ops.tc_tile_windows(owner, geom, inv_rc, num_rbf)
+            owner.win_key = key
+
+
+def _tiles(order, kc, grp_ptr, n_groups, num_rbf, rec, grp_mod):
+    """Greedy tiles of every group; returns (grp_tile [n_groups+1], tile_info, erec, n_tiles)."""
+    dev = order.device
+    counts = ops.tc_plan_count(order, kc, grp_ptr, n_groups, num_rbf)
+    grp_tile = torch.zeros(n_groups + 1, dtype=torch.int32, device=dev)
+    torch.cumsum(counts, 0, dtype=torch.int32, out=grp_tile[1:])
+    n_tiles, n_live = torch.stack([grp_tile[-1], grp_ptr[n_groups]]).tolist()       # one host sync per plan
+    tile_start = ops.tc_plan_fill(order, kc, grp_ptr, n_groups, num_rbf, grp_tile, n_tiles)
+    tile_mod = torch.repeat_interleave(grp_mod.to(torch.int32), counts.long()).contiguous() if n_tiles else \
+        torch.zeros(1, dtype=torch.int32, device=dev)
+    erec, tile_info = ops.tc_plan_finalize(order, tile_start, n_tiles, n_live, rec, tile_mod)
+    return grp_tile, tile_info, erec, n_tiles
+
+
+def _sorted_by_group(kc: Tensor, grp: Tensor, n_groups: int, num_rbf: int):
+    """Edge ids sorted by (group, basis index) with two stable counting sorts; ``grp_ptr [n_groups+2]`` (the last
+    group collects the edges of inactive rows)."""
+    o1 = ops.sort_by_key(kc, num_rbf)[1].long()
+    grp_ptr, o2 = ops.sort_by_key(grp[o1].contiguous(), n_groups + 1)
+    return o1[o2.long()].to(torch.int32).contiguous(), grp_ptr
+
+
+def build_dst_plan(g, geom: Tensor, inv_rc: float, num_rbf: int) -> TilePlan:
+    """Blocks = up to 32 rows of one sub-network: rows ``(atom, slot)`` of 32 consecutive atoms of one
+    (element, owned/ghost) segment and one slot."""
+    dev = geom.device
+    R = ops.tc_block_rows()
+    n, rpa, E = g.n_atoms, g.rows_per_atom, g.n_edges
+    # segments of the internal atom order inside which row_mod only depends on the slot
+    bounds = [0]
+    for t in range(len(g.type_ptr) - 1):
+        lo, hi = g.type_ptr[t], g.type_ptr[t + 1]
+        own = min(max(g.own_count[t] if t < len(g.own_count) else hi - lo, 0), hi - lo)
+        for b in (lo + own, hi):
+            if b > bounds[-1]:
+                bounds.append(b)
+    if bounds[-1] < n:
+        bounds.append(n)
+    seg_lo = torch.tensor(bounds[:-1], dtype=torch.long)
+    seg_hi = torch.tensor(bounds[1:], dtype=torch.long)
+    n_chunks_seg = (seg_hi - seg_lo + R - 1) // R
+    chunk_base = torch.zeros(len(bounds), dtype=torch.long)
+    chunk_base[1:] = torch.cumsum(n_chunks_seg, 0)
+    n_chunks = int(chunk_base[-1])
+    # chunk tables (host, tiny): first atom and size of every chunk
+    seg_of_chunk = torch.repeat_interleave(torch.arange(len(seg_lo)), n_chunks_seg)
+    idx_in_seg = torch.arange(n_chunks) - chunk_base[:-1][seg_of_chunk]
+    chunk_atom0 = (seg_lo[seg_of_chunk] + idx_in_seg * R)
+    chunk_size = torch.minimum(seg_hi[seg_of_chunk] - chunk_atom0, torch.tensor(R))
+    chunk_atom0, chunk_size = chunk_atom0.to(dev), chunk_size.to(dev)
+    n_blocks = n_chunks * rpa
+    slot = torch.arange(rpa, device=dev).view(1, rpa)
+    row0 = (chunk_atom0.view(-1, 1) * rpa + slot)                                   # [n_chunks, rpa]
+    blk_mod = g.row_mod.long()[row0.reshape(-1)] if n_blocks else torch.zeros(0, dtype=torch.long, device=dev)
+    blk_info = torch.stack([row0.reshape(-1), torch.full((n_blocks,), rpa, device=dev, dtype=torch.long),
+                            chunk_size.view(-1, 1).expand(-1, rpa).reshape(-1), blk_mod], 1).to(torch.int32).contiguous()
+    # per atom: chunk and position inside it
+    atom_chunk = torch.repeat_interleave(torch.arange(n_chunks, device=dev), chunk_size.long())
+    atom_local = torch.arange(n, device=dev) - chunk_atom0[atom_chunk]
+    row = g.edge_row.long()
+    atom = torch.div(row, rpa, rounding_mode="floor")
+    blk = atom_chunk[atom] * rpa + (row - atom * rpa)
+    live = g.row_mod.long()[row] >= 0
+    grp = torch.where(live, blk, torch.full_like(blk, n_blocks)).to(torch.int32)
+    kc = ops.tc_basis_index(geom, inv_rc, num_rbf)
+    order, grp_ptr = _sorted_by_group(kc, grp, n_blocks, num_rbf)
+    eid = torch.arange(E, device=dev, dtype=torch.int32)
+    rec = torch.stack([(g.row_xoff[row] + g.col.long()).to(torch.int32), g.col, atom_local[atom].to(torch.int32), eid], 1).contiguous()
+    blk_tile, tile_info, erec, n_tiles = _tiles(order, kc, grp_ptr, n_blocks, num_rbf, rec, blk_mod)
+    plan = TilePlan("dst", blk_info, blk_tile, tile_info, erec, n_blocks, n_tiles, bool((~live).any().item()) if E else False)
+    plan.edge_row_local = None
+    return plan
+
+
+def dst_plan_for_table(plan: TilePlan, g, g0) -> TilePlan:
+    """The first-layer variant of a dst plan: xh rows come from the element table of ``g0`` (hermnet._layer0_tables)."""
+    eid = plan.erec[:, 3].long()
+    erec0 = plan.erec.clone()
+    erec0[:, 0] = (g0.row_xoff[g.edge_row.long()[eid]] + g0.col.long()[eid]).to(torch.int32)
+    return plan.with_erec(erec0.contiguous())
+
+
+def build_src_plan(g, geom: Tensor, inv_rc: float, num_rbf: int) -> TilePlan:
+    """Blocks = 32 consecutive source atoms; groups = (block, sub-network)."""
+    dev = geom.device
+    R = ops.tc_block_rows()
+    n, E, M = g.n_atoms, g.n_edges, g.n_modules
+    n_blocks = (n + R - 1) // R
+    b = torch.arange(n_blocks, device=dev, dtype=torch.long)
+    blk_info = torch.stack([b * R, torch.ones_like(b), torch.clamp(n - b * R, max=R), torch.full_like(b, -1)], 1).to(torch.int32).contiguous()
+    row = g.edge_row.long()
+    mod = g.row_mod.long()[row]
+    col = g.col.long()
+    sblk = torch.div(col, R, rounding_mode="floor")
+    live = mod >= 0
+    n_groups = n_blocks * M
+    grp = torch.where(live, sblk * M + mod, torch.full_like(sblk, n_groups)).to(torch.int32)
+    kc = ops.tc_basis_index(geom, inv_rc, num_rbf)
+    order, grp_ptr = _sorted_by_group(kc, grp, n_groups, num_rbf)
+    eid = torch.arange(E, device=dev, dtype=torch.int32)
+    rec = torch.stack([g.edge_row, (g.row_xoff[row] + col).to(torch.int32), (col - sblk * R).to(torch.int32), eid], 1).contiguous()
+    grp_mod = torch.arange(M, device=dev).repeat(n_blocks)
+    grp_tile, tile_info, erec, n_tiles = _tiles(order, kc, grp_ptr, n_groups, num_rbf, rec, grp_mod)
+    blk_tile = grp_tile[::M].contiguous()
+    return TilePlan("src", blk_info, blk_tile, tile_info, erec, n_blocks, n_tiles, bool((~live).any().item()) if E else False)
+
+
+def plans_of(g, geom: Tensor, inv_rc: float, num_rbf: int, want_src: bool):
+    """Plans cached on the graph (built from the geometry of the first call; later geometries only refresh the windows)."""
+    dst = g._lazy.get("tc_dst")
+    if dst is None:
+        parent = getattr(g, "_tc_parent", None)
+        parent = parent() if parent is not None else None
+        if parent is not None:      # first-layer element-table view of ``parent`` (same rows, edges and geometry)
+            base, _ = plans_of(parent, geom, inv_rc, num_rbf, False)
+            dst = dst_plan_for_table(base, parent, g)
+        else:
+            dst = build_dst_plan(g, geom, inv_rc, num_rbf)
+        g._lazy["tc_dst"] = dst
+    src: Optional[TilePlan] = g._lazy.get("tc_src")
+    if want_src and src is None:
+        src = g._lazy["tc_src"] = build_src_plan(g, geom, inv_rc, num_rbf)
+    return dst, src

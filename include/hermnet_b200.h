@@ -165,6 +165,67 @@ int hn_painn_edge_bwd_w(const hn_edge_params *p, const float *xh, const float *v
                         void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Tensor-core PaiNN edge kernels (tcgen05 / TMEM / TMA; hidden_channels == 128, num_rbf <= 256).
+ * Same arithmetic and reference lines as hn_painn_edge_* above; the filter projection
+ * rbf_proj (HermNet/rmnet.py:45,55) runs as fp16-split (hi + lo) tensor-core tiles with fp32
+ * accumulation: PHI^T[3F x 64 edges] = W^T[3F x 32-wide basis window] . BASIS^T.
+ *
+ * Tile plan (built once per graph, replaces the per-layer regrouping of HermNet/utils.py:11-24):
+ *   a *block* is up to hn_tc_block_rows() rows of ONE sub-network (dst-major: row0 + l*stride) or
+ *   consecutive source atoms (src-major); a *tile* is up to hn_tc_tile_edges() edges of a block
+ *   (src-major: of one (block, sub-network) group) whose Gaussian bands fit one 32-wide window.
+ *     blk_info[n_blocks][4]  dst-major (row0, row stride, n_rows, module | -1), src-major (first atom, 1, n, -1)
+ *     blk_tile[n_blocks+1]   tile range of each block
+ *     tile_info[n_tiles][4]  (first edge record, count, count of records with even local index, module)
+ *     tile_win[n_tiles][2]   (k0, n_chunks): written by hn_tc_tile_windows for the CURRENT geometry
+ *     erec[E][4]             dst-major (xh row, source atom, row_local, edge id),
+ *                            src-major (destination row, xh row of the source, source_local, edge id)
+ *   Build: kc = hn_tc_basis_index(geom); order = edges sorted by (group, kc) (hn_sort_by_key twice);
+ *   hn_tc_plan_count -> caller scans -> hn_tc_plan_fill (tile_start) -> hn_tc_plan_finalize, which
+ *   sorts every tile by (local & 1, local) and writes erec / tile_info from rec[E][4] (indexed by
+ *   edge id, field 2 = local index) and tile_mod[n_tiles].
+ * Weights: hn_tc_split_weights turns Wt [M][K][3F] into fp16 hi and lo planes [2][M*3F][K32],
+ *   K32 = num_rbf rounded up to 32, scaled by a per-module power of two; wscale[m] = 1/scale.
+ * Outputs as in hn_painn_edge_*: fwd dx/dvec (every row of every block is written), bwd_dst one
+ *   g_geom plane [E][4] (only edges in tiles are written), bwd_src grad_xh (zero-filled by the
+ *   caller) and grad_vec (every atom of every block is written).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t n_blocks;
+    int32_t n_tiles;
+    const int32_t *blk_info;
+    const int32_t *blk_tile;
+    const int32_t *tile_info;
+    int32_t *tile_win;
+    const int32_t *erec;
+} hn_tc_plan;
+
+int32_t hn_tc_supported(int32_t hidden, int32_t num_rbf);
+int32_t hn_tc_block_rows(void);
+int32_t hn_tc_tile_edges(void);
+int64_t hn_tc_split_weights_elems(int32_t n_modules, int32_t hidden, int32_t num_rbf);   /* fp16 elements of wsplit */
+int hn_tc_split_weights(const float *Wt, int32_t n_modules, int32_t num_rbf, int32_t hidden, void *wsplit /*fp16*/,
+                        float *wscale /*[M]*/, void *stream);
+int hn_tc_basis_index(const float *geom, int64_t n_edges, float inv_rc, int32_t num_rbf, int32_t *kc /*[E]*/, void *stream);
+int hn_tc_plan_count(const int32_t *order, const int32_t *kc, const int32_t *grp_ptr, int32_t n_groups, int32_t num_rbf,
+                     int32_t *counts /*[n_groups]*/, void *stream);
+int hn_tc_plan_fill(const int32_t *order, const int32_t *kc, const int32_t *grp_ptr, int32_t n_groups, int32_t num_rbf,
+                    const int32_t *grp_tile /*[n_groups+1]*/, int32_t *tile_start /*[n_tiles]*/, void *stream);
+int hn_tc_plan_finalize(const int32_t *order, const int32_t *tile_start, int32_t n_tiles, int64_t n_edges,
+                        const int32_t *rec /*[E][4]*/, const int32_t *tile_mod, int32_t *erec, int32_t *tile_info, void *stream);
+int hn_tc_tile_windows(const hn_tc_plan *plan, const float *geom, float inv_rc, int32_t num_rbf, void *stream);
+int hn_tc_edge_fwd(const hn_edge_params *p, const hn_tc_plan *plan, const float *xh, const float *vec /*NULL: vec == 0*/,
+                   const float *geom, const void *wsplit, const float *wscale, const float *bias, const float *offset,
+                   float *dx, float *dvec, float *dbg /*NULL, or 2*E*3F + 14336 floats: phi | raw accumulators | first operand stage*/,
+                   int64_t dbg_edges /*E of the debug layout*/, void *stream);
+int hn_tc_edge_bwd_dst(const hn_edge_params *p, const hn_tc_plan *plan, const float *xh, const float *vec, const float *geom,
+                       const void *wsplit, const float *wscale, const float *bias, const float *offset, const float *g_dx,
+                       const float *g_dvec, float *g_geom /*[E][4]*/, void *stream);
+int hn_tc_edge_bwd_src(const hn_edge_params *p, const hn_tc_plan *plan /*src-major*/, const float *xh, const float *vec,
+                       const float *geom, const void *wsplit, const float *wscale, const float *bias, const float *offset,
+                       const float *g_dx, const float *g_dvec, float *grad_xh /*zeroed*/, float *grad_vec, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Row gather / segmented sum -- mutually adjoint linear primitives used by the differentiable
  * (double-backward, training) formulation.  Replace PyG's index_select gathers (rmnet.py:58) and
  * torch_scatter.scatter's atomicAdd (rmnet.py:71-72, hermnet.py:130) with deterministic kernels.

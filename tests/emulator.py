@@ -230,6 +230,190 @@ def painn_edge_bwd_w(p, xh, vec, geom, g, offset, g_dx, g_dvec):
     return gW, gb
 
 
+# ---------------------------------------------------------------------------------------------------------
+# tensor-core edge kernels (csrc/hn_edge_tc.cu): the plan builders follow the CUDA kernels step by step and the
+# edge passes walk the PLAN (blocks -> tiles -> edge records, basis restricted to the tile's window), so the host logic
+# of hermnet_b200/tileplan.py and the plan layout are exercised on the CPU
+# ---------------------------------------------------------------------------------------------------------
+TC_TN, TC_KC, TC_ROWS = 64, 32, 32
+
+
+def tc_supported(hidden, num_rbf):
+    return hidden == 128 and 2 <= num_rbf <= 256
+
+
+def tc_block_rows():
+    return TC_ROWS
+
+
+def tc_split_weights(Wt):
+    return Wt.detach().clone(), torch.ones(Wt.size(0), dtype=torch.float32)
+
+
+def tc_basis_index(geom, inv_rc, num_rbf):
+    u = geom.detach()[:, 3] * inv_rc
+    kc = torch.clamp((u * (num_rbf - 1)).to(torch.int32), max=num_rbf - 1)
+    return torch.where(u < 1, kc, torch.full_like(kc, num_rbf - 1)).to(torch.int32)
+
+
+def _tc_fits(kc, k0, K):
+    return kc >= K - 1 or min(kc + 6, K - 1) <= k0 + TC_KC - 1
+
+
+def _tc_window_start(kc, K):
+    return 0 if kc >= K - 1 else (max(kc - 5, 0) & ~7)
+
+
+def _tc_tiles_of_group(ks, K):
+    starts, start, k0 = [], 0, 0
+    for i, k in enumerate(ks):
+        if i == start:
+            k0 = _tc_window_start(k, K)
+        elif i - start >= TC_TN or not _tc_fits(k, k0, K):
+            starts.append(start)
+            start = i
+            k0 = _tc_window_start(k, K)
+    if len(ks):
+        starts.append(start)
+    return starts
+
+
+def tc_plan_count(order, kc, grp_ptr, n_groups, num_rbf):
+    kk = kc[order.long()].tolist()
+    gp = grp_ptr.tolist()
+    return torch.tensor([len(_tc_tiles_of_group(kk[gp[g]:gp[g + 1]], num_rbf)) for g in range(n_groups)], dtype=torch.int32)
+
+
+def tc_plan_fill(order, kc, grp_ptr, n_groups, num_rbf, grp_tile, n_tiles):
+    kk = kc[order.long()].tolist()
+    gp = grp_ptr.tolist()
+    out = []
+    for g in range(n_groups):
+        out += [gp[g] + s for s in _tc_tiles_of_group(kk[gp[g]:gp[g + 1]], num_rbf)]
+    assert len(out) == n_tiles
+    return torch.tensor(out + ([0] if not out else []), dtype=torch.int32)
+
+
+def tc_plan_finalize(order, tile_start, n_tiles, n_edges, rec, tile_mod):
+    erec = torch.zeros((max(n_edges, 1), 4), dtype=torch.int32)
+    info = torch.zeros((max(n_tiles, 1), 4), dtype=torch.int32)
+    ts = tile_start.tolist()
+    for t in range(n_tiles):
+        e0, e1 = ts[t], (ts[t + 1] if t + 1 < n_tiles else n_edges)
+        r = rec[order[e0:e1].long()]
+        key = ((r[:, 2] & 1) << 16) | r[:, 2]
+        o = torch.sort(key, stable=True).indices
+        erec[e0:e1] = r[o]
+        info[t] = torch.tensor([e0, e1 - e0, int(((r[:, 2] & 1) == 0).sum()), int(tile_mod[t])], dtype=torch.int32)
+    return erec, info
+
+
+def tc_tile_windows(plan, geom, inv_rc, num_rbf):
+    K = num_rbf
+    u = geom.detach()[:, 3] * inv_rc
+    for t in range(plan.n_tiles):
+        e0, cnt = int(plan.tile_info[t, 0]), int(plan.tile_info[t, 1])
+        ue = u[plan.erec[e0:e0 + cnt, 3].long()]
+        ue = ue[ue < 1]
+        k0, nchunk = 0, 1
+        if ue.numel():
+            kc = torch.clamp((ue * (K - 1)).to(torch.int32), max=K - 1)
+            k0 = max(int(kc.min()) - 5, 0) & ~7
+            hi = min(int(kc.max()) + 6, K - 1)
+            nchunk = (hi - k0 + TC_KC) // TC_KC
+        plan.tile_win[t, 0], plan.tile_win[t, 1] = k0, nchunk
+
+
+def _tc_records(plan):
+    """Flattened view of a plan: per record (block, tile, window lo, window hi)."""
+    nt = plan.n_tiles
+    info, win = plan.tile_info[:nt].long(), plan.tile_win[:nt].long()
+    cnt = info[:, 1]
+    n = int(cnt.sum())
+    tile_of = torch.repeat_interleave(torch.arange(nt), cnt)
+    assert n == 0 or bool((info[:, 0] == torch.cumsum(cnt, 0) - cnt).all()), "tiles must be contiguous"
+    bt = plan.blk_tile.long()
+    blk_of_tile = torch.repeat_interleave(torch.arange(plan.n_blocks), bt[1:] - bt[:-1])
+    return n, tile_of, blk_of_tile[tile_of], win[tile_of, 0], win[tile_of, 0] + TC_KC * win[tile_of, 1], info[tile_of, 3]
+
+
+def _tc_phi(p, plan, geom, Wt, bias, offset, eid, mod, lo, hi, deriv=False):
+    K = p.num_rbf
+    u = geom[eid, 3] * p.inv_rc
+    pp = p.env_p
+    a, b, c = -0.5 * (pp + 1) * (pp + 2), float(pp * (pp + 2)), -0.5 * pp * (pp + 1)
+    env = 1 + a * u ** pp + b * u ** (pp + 1) + c * u ** (pp + 2)
+    diff = u[:, None] - offset[None, :]
+    gk = torch.exp(p.coeff * diff * diff)
+    k = torch.arange(K)[None, :]
+    inwin = (k >= lo[:, None]) & (k < hi[:, None]) & (u < 1)[:, None]
+    val = torch.where(inwin, env[:, None] * gk, torch.zeros_like(gk))
+    phi = torch.einsum("ek,ekc->ec", val, Wt[mod]) + bias[mod]
+    if not deriv:
+        return phi, None
+    denv = a * pp * u ** (pp - 1) + b * (pp + 1) * u ** pp + c * (pp + 2) * u ** (pp + 1)
+    dval = torch.where(inwin, (denv[:, None] * gk + env[:, None] * gk * (2 * p.coeff * diff)) * p.inv_rc, torch.zeros_like(gk))
+    return phi, torch.einsum("ek,ekc->ec", dval, Wt[mod])
+
+
+def tc_edge_fwd(p, plan, xh, vec, geom, wsplit, wscale, bias, offset, n_rows, debug_phi=False):
+    F = p.hidden
+    assert plan.kind == "dst"
+    if vec is None:
+        vec = torch.zeros((p.n_atoms, 3, F), dtype=xh.dtype)
+    n, tile_of, blk, lo, hi, mod = _tc_records(plan)
+    er = plan.erec[:n].long()
+    bi = plan.blk_info.long()
+    row = bi[blk, 0] + er[:, 2] * bi[blk, 1]
+    assert bool((er[:, 2] < bi[blk, 2]).all()) and bool((mod == bi[blk, 3]).all())
+    phi, _ = _tc_phi(p, plan, geom, wsplit, bias, offset, er[:, 3], mod, lo, hi)
+    c1, c2 = 1 / math.sqrt(3.0 * F), 1 / math.sqrt(F)
+    a, b, c = torch.split(xh[er[:, 0]] * phi, F, dim=-1)
+    mv = vec[er[:, 1]] * (b * c1)[:, None, :] + (c * c2)[:, None, :] * geom[er[:, 3], :3, None]
+    dx = torch.zeros((n_rows, F), dtype=xh.dtype).index_add_(0, row, a)
+    dvec = torch.zeros((n_rows, 3, F), dtype=xh.dtype).index_add_(0, row, mv)
+    return dx, dvec
+
+
+def tc_edge_bwd_dst(p, plan, xh, vec, geom, wsplit, wscale, bias, offset, g_dx, g_dvec):
+    F = p.hidden
+    if vec is None:
+        vec = torch.zeros((p.n_atoms, 3, F), dtype=xh.dtype)
+    n, tile_of, blk, lo, hi, mod = _tc_records(plan)
+    er = plan.erec[:n].long()
+    bi = plan.blk_info.long()
+    row = bi[blk, 0] + er[:, 2] * bi[blk, 1]
+    phi, dphi = _tc_phi(p, plan, geom, wsplit, bias, offset, er[:, 3], mod, lo, hi, deriv=True)
+    gm = geom[er[:, 3]]
+    gv, tb, tc, c1, c2 = _t_terms(p, vec[er[:, 1]], gm, g_dvec, row, F)
+    Pa, Pb, Pc = torch.split(xh[er[:, 0]], F, dim=-1)
+    da, db, dc = torch.split(dphi, F, dim=-1)
+    gd = (g_dx[row] * Pa * da + tb * Pb * db + tc * Pc * dc).sum(1)
+    gu = (gv * (Pc * phi[:, 2 * F:] * c2)[:, None, :]).sum(2)
+    out = torch.zeros((1, geom.size(0), 4), dtype=xh.dtype)
+    out[0, er[:, 3]] = torch.cat([gu, gd[:, None]], 1)
+    return out
+
+
+def tc_edge_bwd_src(p, plan, xh, vec, geom, wsplit, wscale, bias, offset, g_dx, g_dvec):
+    F = p.hidden
+    assert plan.kind == "src"
+    n, tile_of, blk, lo, hi, mod = _tc_records(plan)
+    er = plan.erec[:n].long()
+    bi = plan.blk_info.long()
+    s = bi[blk, 0] + er[:, 2]
+    row = er[:, 0]
+    phi, _ = _tc_phi(p, plan, geom, wsplit, bias, offset, er[:, 3], mod, lo, hi)
+    gm = geom[er[:, 3]]
+    gv, tb, tc, c1, c2 = _t_terms(p, vec[s], gm, g_dvec, row, F)
+    fa, fb, fc = torch.split(phi, F, dim=-1)
+    gP = torch.cat([g_dx[row] * fa, tb * fb, tc * fc], 1)
+    grad_xh = torch.zeros_like(xh).index_add_(0, er[:, 1], gP)
+    bphi = xh[er[:, 1]][:, F:2 * F] * fb * c1
+    grad_vec = torch.zeros_like(vec).index_add_(0, s, gv * bphi[:, None, :])
+    return grad_xh, grad_vec
+
+
 def gather_rows(X, idx):
     return X[idx.long()].contiguous()
 
@@ -330,7 +514,9 @@ def install(monkeypatch):
     for name in ("radius_graph", "sort_by_key", "expand_rowptr", "triplets", "triplet_dots", "edge_geom_fwd",
                  "edge_geom_bwd", "edge_params", "edge_num_slices", "painn_edge_fwd", "painn_edge_bwd_dst",
                  "painn_edge_bwd_src", "painn_edge_bwd_w", "gemm_tf32x3_ex", "node_pre", "node_mid", "node_post",
-                 "node_post_bwd", "node_mid_bwd", "node_pre_bwd", "gather_rows", "segment_sum", "gemm_tf32x3", "split_tf32"):
+                 "node_post_bwd", "node_mid_bwd", "node_pre_bwd", "gather_rows", "segment_sum", "gemm_tf32x3", "split_tf32",
+                 "tc_supported", "tc_block_rows", "tc_split_weights", "tc_basis_index", "tc_plan_count", "tc_plan_fill",
+                 "tc_plan_finalize", "tc_tile_windows", "tc_edge_fwd", "tc_edge_bwd_dst", "tc_edge_bwd_src"):
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(ops, "require_cuda", lambda t, what: None)
     monkeypatch.setattr(ops, "compute_device", lambda t: t.device)

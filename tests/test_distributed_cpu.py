@@ -35,11 +35,11 @@ def _init(rank, world, port):
     torch.set_num_threads(2)
 
 
-def _dd_worker(rank, world, port, kind, out):
+def _dd_worker(rank, world, port, kind, out, intensive=False):
     _init(rank, world, port)
     pos, Z, cell = synthetic.cubic_lattice(8, 2.3, ("Li", "Si", "O"), (1 / 3, 1 / 6, 1 / 2), 0.1, 5)
     cfg = dict(elems=["Li", "Si", "O"], rc=4.0, num_layers=3, hidden_channels=32, num_rbf=32)
-    model, _ = util.make_model(kind, cfg, 9)
+    model, _ = util.make_model(kind, cfg, 9, intensive=intensive)
     p, z, c = torch.from_numpy(pos), torch.from_numpy(Z), torch.from_numpy(cell)[None]
     dd = parallel.DomainDecomposition(model, torch.device("cpu")).build(p, z, c)
     e, g = dd.energy_forces(p)
@@ -49,14 +49,15 @@ def _dd_worker(rank, world, port, kind, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,kind", [(2, "HVNet"), (4, "HVNet"), (2, "HPNet"), (2, "HTNet")])
-def test_domain_decomposition_equals_single_process(emu, tmp_path, world, kind):
+@pytest.mark.parametrize("world,kind,intensive", [(2, "HVNet", False), (4, "HVNet", False), (2, "HPNet", False),
+                                                  (2, "HTNet", False), (2, "HVNet", True)])
+def test_domain_decomposition_equals_single_process(emu, tmp_path, world, kind, intensive):
     out = str(tmp_path / "dd.pt")
-    mp.spawn(_dd_worker, args=(world, _free_port(), kind, out), nprocs=world, join=True)
+    mp.spawn(_dd_worker, args=(world, _free_port(), kind, out, intensive), nprocs=world, join=True)
     got = torch.load(out)
     pos, Z, cell = synthetic.cubic_lattice(8, 2.3, ("Li", "Si", "O"), (1 / 3, 1 / 6, 1 / 2), 0.1, 5)
     cfg = dict(elems=["Li", "Si", "O"], rc=4.0, num_layers=3, hidden_channels=32, num_rbf=32)
-    model, _ = util.make_model(kind, cfg, 9)
+    model, _ = util.make_model(kind, cfg, 9, intensive=intensive)
     d = H.Data(pos=torch.from_numpy(pos).requires_grad_(True), atomic_number=torch.from_numpy(Z),
                cell=torch.from_numpy(cell)[None])
     e = model(d)
