@@ -53,6 +53,7 @@ SIGNATURES = {
     "hn_tc_supported": (c_int32, [c_int32, c_int32]),
     "hn_tc_block_rows": (c_int32, []),
     "hn_tc_tile_edges": (c_int32, []),
+    "hn_tc_groups": (c_int32, []),
     "hn_tc_split_weights_elems": (c_int64, [c_int32, c_int32, c_int32]),
     "hn_tc_split_weights": (c_int32, [P, c_int32, c_int32, c_int32, P, P, P]),
     "hn_tc_basis_index": (c_int32, [P, c_int64, c_float, c_int32, P, P]),

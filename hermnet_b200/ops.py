@@ -480,6 +480,10 @@ def tc_block_rows() -> int:
     return int(_lib.load().hn_tc_block_rows())
 
 
+def tc_groups() -> int:
+    return int(_lib.load().hn_tc_groups())
+
+
 def tc_split_weights(Wt: Tensor):
     """``Wt [M,K,3F]`` -> fp16 (hi | lo) rows ``[M*3F, 2, K32]`` scaled by a per-module power of two, ``wscale [M]``."""
     lib = _lib.load()

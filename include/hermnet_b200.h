@@ -176,13 +176,13 @@ int hn_painn_edge_bwd_w(const hn_edge_params *p, const float *xh, const float *v
  *   (src-major: of one (block, sub-network) group) whose Gaussian bands fit one 32-wide window.
  *     blk_info[n_blocks][4]  dst-major (row0, row stride, n_rows, module | -1), src-major (first atom, 1, n, -1)
  *     blk_tile[n_blocks+1]   tile range of each block
- *     tile_info[n_tiles][4]  (first edge record, count, count of records with even local index, module)
+ *     tile_info[n_tiles][4]  (first edge record, count, cumulative ends of the (local % G) groups packed 8 bits each, module)
  *     tile_win[n_tiles][2]   (k0, n_chunks): written by hn_tc_tile_windows for the CURRENT geometry
  *     erec[E][4]             dst-major (xh row, source atom, row_local, edge id),
  *                            src-major (destination row, xh row of the source, source_local, edge id)
  *   Build: kc = hn_tc_basis_index(geom); order = edges sorted by (group, kc) (hn_sort_by_key twice);
  *   hn_tc_plan_count -> caller scans -> hn_tc_plan_fill (tile_start) -> hn_tc_plan_finalize, which
- *   sorts every tile by (local & 1, local) and writes erec / tile_info from rec[E][4] (indexed by
+ *   sorts every tile by (local % G, local) and writes erec / tile_info from rec[E][4] (indexed by
  *   edge id, field 2 = local index) and tile_mod[n_tiles].
  * Weights: hn_tc_split_weights turns Wt [M][K][3F] into fp16 hi and lo planes [2][M*3F][K32],
  *   K32 = num_rbf rounded up to 32, scaled by a per-module power of two; wscale[m] = 1/scale.
@@ -203,6 +203,7 @@ typedef struct {
 int32_t hn_tc_supported(int32_t hidden, int32_t num_rbf);
 int32_t hn_tc_block_rows(void);
 int32_t hn_tc_tile_edges(void);
+int32_t hn_tc_groups(void);          /* epilogue groups G: tiles are sorted by (local % G, local) */
 int64_t hn_tc_split_weights_elems(int32_t n_modules, int32_t hidden, int32_t num_rbf);   /* fp16 elements of wsplit */
 int hn_tc_split_weights(const float *Wt, int32_t n_modules, int32_t num_rbf, int32_t hidden, void *wsplit /*fp16*/,
                         float *wscale /*[M]*/, void *stream);

@@ -235,7 +235,7 @@ def painn_edge_bwd_w(p, xh, vec, geom, g, offset, g_dx, g_dvec):
 # edge passes walk the PLAN (blocks -> tiles -> edge records, basis restricted to the tile's window), so the host logic
 # of hermnet_b200/tileplan.py and the plan layout are exercised on the CPU
 # ---------------------------------------------------------------------------------------------------------
-TC_TN, TC_KC, TC_ROWS = 64, 32, 32
+TC_TN, TC_KC, TC_ROWS, TC_NG = 64, 32, 32, 3
 
 
 def tc_supported(hidden, num_rbf):
@@ -244,6 +244,10 @@ def tc_supported(hidden, num_rbf):
 
 def tc_block_rows():
     return TC_ROWS
+
+
+def tc_groups():
+    return TC_NG
 
 
 def tc_split_weights(Wt):
@@ -301,10 +305,11 @@ def tc_plan_finalize(order, tile_start, n_tiles, n_edges, rec, tile_mod):
     for t in range(n_tiles):
         e0, e1 = ts[t], (ts[t + 1] if t + 1 < n_tiles else n_edges)
         r = rec[order[e0:e1].long()]
-        key = ((r[:, 2] & 1) << 16) | r[:, 2]
+        key = ((r[:, 2] % TC_NG) << 16) | r[:, 2]
         o = torch.sort(key, stable=True).indices
         erec[e0:e1] = r[o]
-        info[t] = torch.tensor([e0, e1 - e0, int(((r[:, 2] & 1) == 0).sum()), int(tile_mod[t])], dtype=torch.int32)
+        split = sum(int(((r[:, 2] % TC_NG) <= gq).sum()) << (8 * gq) for gq in range(TC_NG - 1))
+        info[t] = torch.tensor([e0, e1 - e0, split, int(tile_mod[t])], dtype=torch.int32)
     return erec, info
 
 
@@ -515,7 +520,7 @@ def install(monkeypatch):
                  "edge_geom_bwd", "edge_params", "edge_num_slices", "painn_edge_fwd", "painn_edge_bwd_dst",
                  "painn_edge_bwd_src", "painn_edge_bwd_w", "gemm_tf32x3_ex", "node_pre", "node_mid", "node_post",
                  "node_post_bwd", "node_mid_bwd", "node_pre_bwd", "gather_rows", "segment_sum", "gemm_tf32x3", "split_tf32",
-                 "tc_supported", "tc_block_rows", "tc_split_weights", "tc_basis_index", "tc_plan_count", "tc_plan_fill",
+                 "tc_supported", "tc_block_rows", "tc_groups", "tc_split_weights", "tc_basis_index", "tc_plan_count", "tc_plan_fill",
                  "tc_plan_finalize", "tc_tile_windows", "tc_edge_fwd", "tc_edge_bwd_dst", "tc_edge_bwd_src"):
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(ops, "require_cuda", lambda t, what: None)

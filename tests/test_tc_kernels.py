@@ -14,7 +14,8 @@ from tests.util import edge_inputs as _edge_inputs, frozen_model as _model, latt
 
 def check_plan(plan, g, geom, K, inv_rc):
     """Every live row-edge is in exactly one tile; tiles hold <= 64 edges of one block / group, sorted by
-    (local & 1, local); the window of every tile covers the 12-wide band of each of its in-range edges."""
+    (local % G, local); the window of every tile covers the 12-wide band of each of its in-range edges."""
+    NG = ops.tc_groups()
     nt = plan.n_tiles
     info = plan.tile_info[:nt].cpu().long()
     win = plan.tile_win[:nt].cpu().long()
@@ -47,11 +48,13 @@ def check_plan(plan, g, geom, K, inv_rc):
         assert torch.equal(info[tile_of, 3], g.row_mod.cpu().long()[row[eids]])
     assert torch.equal(erec[:n, 1 if plan.kind == "src" else 0], (g.row_xoff.cpu()[row[eids]] + g.col.cpu().long()[eids]))
     # order inside a tile, even count
-    key = ((loc & 1) << 16) | loc
+    key = ((loc % NG) << 16) | loc
     same = tile_of[1:] == tile_of[:-1]
     assert bool((key[1:][same] >= key[:-1][same]).all())
-    n_even = torch.zeros(nt, dtype=torch.long).index_add_(0, tile_of, ((loc & 1) == 0).long())
-    assert torch.equal(n_even, info[:, 2])
+    split = torch.zeros(nt, dtype=torch.long)
+    for gq in range(NG - 1):
+        split += torch.zeros(nt, dtype=torch.long).index_add_(0, tile_of, ((loc % NG) <= gq).long()) << (8 * gq)
+    assert torch.equal(split, info[:, 2])
     # windows
     u = geom.cpu()[eids, 3] * inv_rc
     kc = torch.clamp((u * (K - 1)).to(torch.int64), max=K - 1)
