@@ -13,7 +13,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
-LIB_PATH = os.path.join(LIB_DIR, "libhermnet_b200.so")
+# HERMNET_B200_LIB: load / build another file instead (A/B builds made with HERMNET_B200_NVCC_FLAGS)
+LIB_PATH = os.environ.get("HERMNET_B200_LIB") or os.path.join(LIB_DIR, "libhermnet_b200.so")
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared", "-diag-suppress", "549"]
 

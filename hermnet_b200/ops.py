@@ -476,8 +476,8 @@ def tc_supported(hidden: int, num_rbf: int) -> bool:
     return bool(_lib.load().hn_tc_supported(int(hidden), int(num_rbf)))
 
 
-def tc_block_rows() -> int:
-    return int(_lib.load().hn_tc_block_rows())
+def tc_block_rows(src_major: bool = False) -> int:
+    return int(_lib.load().hn_tc_block_rows(1 if src_major else 0))
 
 
 def tc_groups() -> int:

@@ -20,24 +20,30 @@ Tensor = torch.Tensor
 
 
 class TilePlan:
-    def __init__(self, kind: str, blk_info, blk_tile, tile_info, erec, n_blocks: int, n_tiles: int, has_inactive: bool):
+    def __init__(self, kind: str, blk_info, blk_tile, tile_info, erec, n_blocks: int, n_tiles: int, has_inactive: bool,
+                 blk_xoff=None):
         self.kind = kind
         self.blk_info, self.blk_tile, self.tile_info, self.erec = blk_info, blk_tile, tile_info, erec
+        # dst-major: the xh row of source s for the rows of block b is blk_xoff[b] + s
+        self.blk_xoff = blk_xoff if blk_xoff is not None else torch.zeros(max(n_blocks, 1), dtype=torch.int32, device=erec.device)
         self.n_blocks, self.n_tiles, self.has_inactive = n_blocks, n_tiles, has_inactive
         self.tile_win = torch.zeros((max(n_tiles, 1), 2), dtype=torch.int32, device=erec.device)
+        self.tile_geom = torch.zeros((erec.size(0), 4), dtype=torch.float32, device=erec.device)
         self.win_key = None        # (data_ptr, version) of the geometry the windows were computed for
         self._c = None
 
     def cstruct(self) -> TcPlan:
         if self._c is None:
             self._c = TcPlan(self.n_blocks, self.n_tiles, self.blk_info.data_ptr(), self.blk_tile.data_ptr(),
-                             self.tile_info.data_ptr(), self.tile_win.data_ptr(), self.erec.data_ptr())
+                             self.blk_xoff.data_ptr(), self.tile_info.data_ptr(), self.tile_win.data_ptr(),
+                             self.erec.data_ptr(), self.tile_geom.data_ptr())
         return self._c
 
-    def with_erec(self, erec: Tensor) -> "TilePlan":
+    def with_erec(self, erec: Tensor, blk_xoff: Tensor) -> "TilePlan":
         """Same tiling, different edge records (first-layer element table)."""
-        q = TilePlan(self.kind, self.blk_info, self.blk_tile, self.tile_info, erec, self.n_blocks, self.n_tiles, self.has_inactive)
-        q.tile_win = self.tile_win          # shared: the windows only depend on the geometry
+        q = TilePlan(self.kind, self.blk_info, self.blk_tile, self.tile_info, erec, self.n_blocks, self.n_tiles,
+                     self.has_inactive, blk_xoff)
+        q.tile_win, q.tile_geom = self.tile_win, self.tile_geom          # shared: they only depend on the geometry
         q._shared_with = self
         return q
 
@@ -75,8 +81,10 @@ def build_dst_plan(g, geom: Tensor, inv_rc: float, num_rbf: int) -> TilePlan:
     """Blocks = up to 32 rows of one sub-network: rows ``(atom, slot)`` of 32 consecutive atoms of one
     (element, owned/ghost) segment and one slot."""
     dev = geom.device
-    R = ops.tc_block_rows()
+    R = ops.tc_block_rows(False)
     n, rpa, E = g.n_atoms, g.rows_per_atom, g.n_edges
+    if n >= (1 << 27):
+        raise RuntimeError("hermnet_b200: the tensor-core tile plan supports fewer than 2^27 atoms per rank")
     # segments of the internal atom order inside which row_mod only depends on the slot
     bounds = [0]
     for t in range(len(g.type_ptr) - 1):
@@ -118,23 +126,25 @@ def build_dst_plan(g, geom: Tensor, inv_rc: float, num_rbf: int) -> TilePlan:
     eid = torch.arange(E, device=dev, dtype=torch.int32)
     rec = torch.stack([(g.row_xoff[row] + g.col.long()).to(torch.int32), g.col, atom_local[atom].to(torch.int32), eid], 1).contiguous()
     blk_tile, tile_info, erec, n_tiles = _tiles(order, kc, grp_ptr, n_blocks, num_rbf, rec, blk_mod)
-    plan = TilePlan("dst", blk_info, blk_tile, tile_info, erec, n_blocks, n_tiles, bool((~live).any().item()) if E else False)
-    plan.edge_row_local = None
-    return plan
+    blk_xoff = g.row_xoff[row0.reshape(-1)].to(torch.int32).contiguous() if n_blocks else None
+    return TilePlan("dst", blk_info, blk_tile, tile_info, erec, n_blocks, n_tiles, bool((~live).any().item()) if E else False,
+                    blk_xoff)
 
 
 def dst_plan_for_table(plan: TilePlan, g, g0) -> TilePlan:
     """The first-layer variant of a dst plan: xh rows come from the element table of ``g0`` (hermnet._layer0_tables)."""
     eid = plan.erec[:, 3].long()
     erec0 = plan.erec.clone()
+    erec0[:, 1] = g0.col[eid]                     # the "source" the kernels index xh with is the source's ELEMENT row
     erec0[:, 0] = (g0.row_xoff[g.edge_row.long()[eid]] + g0.col.long()[eid]).to(torch.int32)
-    return plan.with_erec(erec0.contiguous())
+    blk_xoff0 = g0.row_xoff[plan.blk_info[:, 0].long()].to(torch.int32).contiguous()
+    return plan.with_erec(erec0.contiguous(), blk_xoff0)
 
 
 def build_src_plan(g, geom: Tensor, inv_rc: float, num_rbf: int) -> TilePlan:
     """Blocks = 32 consecutive source atoms; groups = (block, sub-network)."""
     dev = geom.device
-    R = ops.tc_block_rows()
+    R = ops.tc_block_rows(True)
     n, E, M = g.n_atoms, g.n_edges, g.n_modules
     n_blocks = (n + R - 1) // R
     b = torch.arange(n_blocks, device=dev, dtype=torch.long)

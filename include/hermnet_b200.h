@@ -171,13 +171,14 @@ int hn_painn_edge_bwd_w(const hn_edge_params *p, const float *xh, const float *v
  * accumulation: PHI^T[3F x 64 edges] = W^T[3F x 32-wide basis window] . BASIS^T.
  *
  * Tile plan (built once per graph, replaces the per-layer regrouping of HermNet/utils.py:11-24):
- *   a *block* is up to hn_tc_block_rows() rows of ONE sub-network (dst-major: row0 + l*stride) or
+ *   a *block* is up to hn_tc_block_rows(0|1) rows of ONE sub-network (dst-major: row0 + l*stride) or
  *   consecutive source atoms (src-major); a *tile* is up to hn_tc_tile_edges() edges of a block
  *   (src-major: of one (block, sub-network) group) whose Gaussian bands fit one 32-wide window.
  *     blk_info[n_blocks][4]  dst-major (row0, row stride, n_rows, module | -1), src-major (first atom, 1, n, -1)
  *     blk_tile[n_blocks+1]   tile range of each block
  *     tile_info[n_tiles][4]  (first edge record, count, cumulative ends of the (local % G) groups packed 8 bits each, module)
- *     tile_win[n_tiles][2]   (k0, n_chunks): written by hn_tc_tile_windows for the CURRENT geometry
+ *     tile_win[n_tiles][2]   (k0, n_chunks): written by hn_tc_tile_windows for the CURRENT geometry, together with
+ *     tile_geom[E][4]        the geometry (ux,uy,uz,d) of every record in record order (the kernels read THIS, not geom)
  *     erec[E][4]             dst-major (xh row, source atom, row_local, edge id),
  *                            src-major (destination row, xh row of the source, source_local, edge id)
  *   Build: kc = hn_tc_basis_index(geom); order = edges sorted by (group, kc) (hn_sort_by_key twice);
@@ -195,13 +196,15 @@ typedef struct {
     int32_t n_tiles;
     const int32_t *blk_info;
     const int32_t *blk_tile;
+    const int32_t *blk_xoff;   /* dst-major [n_blocks]: xh row of source s for the block's rows = blk_xoff[b] + erec[.][1] */
     const int32_t *tile_info;
     int32_t *tile_win;
     const int32_t *erec;
+    float *tile_geom;          /* [E][4]: geometry of every record, written by hn_tc_tile_windows */
 } hn_tc_plan;
 
 int32_t hn_tc_supported(int32_t hidden, int32_t num_rbf);
-int32_t hn_tc_block_rows(void);
+int32_t hn_tc_block_rows(int32_t src_major);   /* rows (dst-major) / source atoms (src-major) per block */
 int32_t hn_tc_tile_edges(void);
 int32_t hn_tc_groups(void);          /* epilogue groups G: tiles are sorted by (local % G, local) */
 int64_t hn_tc_split_weights_elems(int32_t n_modules, int32_t hidden, int32_t num_rbf);   /* fp16 elements of wsplit */

@@ -235,15 +235,15 @@ def painn_edge_bwd_w(p, xh, vec, geom, g, offset, g_dx, g_dvec):
 # edge passes walk the PLAN (blocks -> tiles -> edge records, basis restricted to the tile's window), so the host logic
 # of hermnet_b200/tileplan.py and the plan layout are exercised on the CPU
 # ---------------------------------------------------------------------------------------------------------
-TC_TN, TC_KC, TC_ROWS, TC_NG = 64, 32, 32, 3
+TC_TN, TC_KC, TC_ROWS_DST, TC_ROWS_SRC, TC_NG = 64, 32, 12, 32, 3
 
 
 def tc_supported(hidden, num_rbf):
     return hidden == 128 and 2 <= num_rbf <= 256
 
 
-def tc_block_rows():
-    return TC_ROWS
+def tc_block_rows(src_major=False):
+    return TC_ROWS_SRC if src_major else TC_ROWS_DST
 
 
 def tc_groups():
@@ -327,6 +327,7 @@ def tc_tile_windows(plan, geom, inv_rc, num_rbf):
             hi = min(int(kc.max()) + 6, K - 1)
             nchunk = (hi - k0 + TC_KC) // TC_KC
         plan.tile_win[t, 0], plan.tile_win[t, 1] = k0, nchunk
+        plan.tile_geom[e0:e0 + cnt] = geom.detach()[plan.erec[e0:e0 + cnt, 3].long()]
 
 
 def _tc_records(plan):
@@ -344,7 +345,7 @@ def _tc_records(plan):
 
 def _tc_phi(p, plan, geom, Wt, bias, offset, eid, mod, lo, hi, deriv=False):
     K = p.num_rbf
-    u = geom[eid, 3] * p.inv_rc
+    u = geom[:, 3] * p.inv_rc
     pp = p.env_p
     a, b, c = -0.5 * (pp + 1) * (pp + 2), float(pp * (pp + 2)), -0.5 * pp * (pp + 1)
     env = 1 + a * u ** pp + b * u ** (pp + 1) + c * u ** (pp + 2)
@@ -371,10 +372,12 @@ def tc_edge_fwd(p, plan, xh, vec, geom, wsplit, wscale, bias, offset, n_rows, de
     bi = plan.blk_info.long()
     row = bi[blk, 0] + er[:, 2] * bi[blk, 1]
     assert bool((er[:, 2] < bi[blk, 2]).all()) and bool((mod == bi[blk, 3]).all())
-    phi, _ = _tc_phi(p, plan, geom, wsplit, bias, offset, er[:, 3], mod, lo, hi)
+    tg = plan.tile_geom[:n]                      # the kernels read the geometry in record order (hn_tc_tile_windows)
+    phi, _ = _tc_phi(p, plan, tg, wsplit, bias, offset, er[:, 3], mod, lo, hi)
     c1, c2 = 1 / math.sqrt(3.0 * F), 1 / math.sqrt(F)
-    a, b, c = torch.split(xh[er[:, 0]] * phi, F, dim=-1)
-    mv = vec[er[:, 1]] * (b * c1)[:, None, :] + (c * c2)[:, None, :] * geom[er[:, 3], :3, None]
+    xrow = plan.blk_xoff.long()[blk] + er[:, 1]              # the kernels index xh with (block offset + source index)
+    a, b, c = torch.split(xh[xrow] * phi, F, dim=-1)
+    mv = vec[er[:, 1]] * (b * c1)[:, None, :] + (c * c2)[:, None, :] * tg[:, :3, None]
     dx = torch.zeros((n_rows, F), dtype=xh.dtype).index_add_(0, row, a)
     dvec = torch.zeros((n_rows, 3, F), dtype=xh.dtype).index_add_(0, row, mv)
     return dx, dvec
@@ -388,10 +391,10 @@ def tc_edge_bwd_dst(p, plan, xh, vec, geom, wsplit, wscale, bias, offset, g_dx, 
     er = plan.erec[:n].long()
     bi = plan.blk_info.long()
     row = bi[blk, 0] + er[:, 2] * bi[blk, 1]
-    phi, dphi = _tc_phi(p, plan, geom, wsplit, bias, offset, er[:, 3], mod, lo, hi, deriv=True)
-    gm = geom[er[:, 3]]
+    gm = plan.tile_geom[:n]
+    phi, dphi = _tc_phi(p, plan, gm, wsplit, bias, offset, er[:, 3], mod, lo, hi, deriv=True)
     gv, tb, tc, c1, c2 = _t_terms(p, vec[er[:, 1]], gm, g_dvec, row, F)
-    Pa, Pb, Pc = torch.split(xh[er[:, 0]], F, dim=-1)
+    Pa, Pb, Pc = torch.split(xh[plan.blk_xoff.long()[blk] + er[:, 1]], F, dim=-1)
     da, db, dc = torch.split(dphi, F, dim=-1)
     gd = (g_dx[row] * Pa * da + tb * Pb * db + tc * Pc * dc).sum(1)
     gu = (gv * (Pc * phi[:, 2 * F:] * c2)[:, None, :]).sum(2)
@@ -408,8 +411,8 @@ def tc_edge_bwd_src(p, plan, xh, vec, geom, wsplit, wscale, bias, offset, g_dx, 
     bi = plan.blk_info.long()
     s = bi[blk, 0] + er[:, 2]
     row = er[:, 0]
-    phi, _ = _tc_phi(p, plan, geom, wsplit, bias, offset, er[:, 3], mod, lo, hi)
-    gm = geom[er[:, 3]]
+    gm = plan.tile_geom[:n]
+    phi, _ = _tc_phi(p, plan, gm, wsplit, bias, offset, er[:, 3], mod, lo, hi)
     gv, tb, tc, c1, c2 = _t_terms(p, vec[s], gm, g_dvec, row, F)
     fa, fb, fc = torch.split(phi, F, dim=-1)
     gP = torch.cat([g_dx[row] * fa, tb * fb, tc * fc], 1)

@@ -39,6 +39,7 @@ def check_plan(plan, g, geom, K, inv_rc):
     loc = erec[:n, 2]
     assert bool((loc >= 0).all()) and bool((loc < bi[blk, 2]).all())
     if plan.kind == "dst":
+        assert torch.equal(plan.blk_xoff.cpu().long()[blk] + erec[:n, 1], erec[:n, 0])
         assert torch.equal(bi[blk, 0] + loc * bi[blk, 1], row[eids])
         assert torch.equal(erec[:n, 1], g.col.cpu().long()[eids])
         assert torch.equal(info[tile_of, 3], g.row_mod.cpu().long()[row[eids]])
