@@ -96,18 +96,47 @@ class _HermNet(nn.Module):
         """Device neighbour search + row CSR for this model (replaces data.py:14-24 and utils.py:11-24)."""
         return self.builder.from_positions(pos, atomic_number, cell, batch)
 
+    @staticmethod
+    def _input_key(data, names):
+        """Identity + version of the tensors a cached graph was derived from (weak references: ids and addresses are
+        recycled).  In-place edits bump ``_version``; re-assigned attributes are different objects."""
+        refs = []
+        for n in names:
+            t = data.get(n)
+            refs.append(None if t is None else (weakref.ref(t), t._version, tuple(t.shape)))
+        return refs
+
+    @staticmethod
+    def _key_matches(key, data, names) -> bool:
+        for n, k in zip(names, key):
+            t = data.get(n)
+            if (t is None) != (k is None):
+                return False
+            if t is not None and (k[0]() is not t or k[1] != t._version or k[2] != tuple(t.shape)):
+                return False
+        return True
+
     def _graph_of(self, data) -> RowGraph:
+        """The row CSR of ``data``.  A graph the CALLER attached (``data.graph = model.build_graph(...)``) is trusted as
+        is; a graph this method attached itself is only re-used while the tensors it was derived from (``edge_index`` /
+        ``edge_shift`` when given -- the reference always honours the current ones, hermnet.py:134-139 -- otherwise
+        ``pos`` / ``cell``) are the same objects at the same version."""
         g = data.get("graph") if hasattr(data, "get") else getattr(data, "graph", None)
         n = data.pos.size(0)
-        if isinstance(g, RowGraph) and g.kind == self.KIND and g.n_atoms == n and g.sign == self.builder.sign:
-            return g
-        batch = data.get("batch")
         ei = data.get("edge_index")
+        names = ("atomic_number", "batch", "edge_index", "edge_shift") if ei is not None else \
+            ("atomic_number", "batch", "pos", "cell")
+        if isinstance(g, RowGraph) and g.kind == self.KIND and g.n_atoms == n and g.sign == self.builder.sign:
+            key = getattr(g, "_auto_key", None)
+            if key is None or (key[0] == names and self._key_matches(key[1], data, names)):
+                return g
+        batch = data.get("batch")
         if ei is not None:
             g = self.builder.from_edge_index(data.atomic_number, ei, data.get("edge_shift"), batch,
                                              pos=data.pos, cell=data.get("cell"))
         else:
             g = self.builder.from_positions(data.pos, data.atomic_number, data.get("cell"), batch)
+        g._auto_key = (names, self._input_key(data, names))
         data.graph = g
         return g
 

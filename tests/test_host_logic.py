@@ -163,3 +163,41 @@ def test_layer_checkpointing_gives_identical_energy_and_forces(emu):
         assert all(torch.equal(a, b) for a, b in zip(*out))
         model.checkpoint_layers = None
         assert model._want_checkpoint(model.build_graph(pos, Z, cell), pos) is False      # CPU tensors: never
+
+
+def test_auto_attached_graph_follows_the_current_inputs(emu):
+    """a graph that forward() attached to ``data`` itself must not outlive the tensors it was derived from
+    (the reference always honours the current pos / edge_index, hermnet.py:134-139); a caller-attached graph is kept."""
+    case = util.load_case("c1_hvnet")
+    model, _ = util.make_model(case["kind"], case["cfg"], case["seed"])
+    data = util.make_data(case, with_edges=False, requires_grad=False)
+    e0 = model(data)
+    g0 = data.graph
+    assert model(data) is not None and data.graph is g0                      # unchanged inputs: re-used
+    with torch.no_grad():
+        data.pos[::3] += 0.8                                                 # in-place move: some pairs cross the cutoff
+    e1 = model(data)
+    assert data.graph is not g0
+    fresh = util.make_data(case, with_edges=False, requires_grad=False)
+    fresh.pos = data.pos.clone()
+    assert util.rel_err(e1.detach(), model(fresh).detach()) < 1e-6
+    assert abs(float(e1) - float(e0)) > 1e-4
+    data.pos = data.pos.clone()                                              # re-assigned attribute: rebuilt, same answer
+    g1 = data.graph
+    e2 = model(data)
+    assert data.graph is not g1 and util.rel_err(e2.detach(), e1.detach()) < 1e-6
+    # explicit edge lists: keyed on edge_index / edge_shift, not on pos
+    d2 = util.make_data(case, with_edges=True, requires_grad=False)
+    model(d2)
+    g2 = d2.graph
+    keep = torch.ones(d2.edge_index.size(1), dtype=torch.bool)
+    keep[::7] = False
+    d2.edge_index, d2.edge_shift = d2.edge_index[:, keep], d2.edge_shift[keep]
+    model(d2)
+    assert d2.graph is not g2 and d2.graph.n_edges == int(keep.sum())
+    # a graph the caller attached is trusted as is
+    d3 = util.make_data(case, with_edges=False, requires_grad=False)
+    d3.graph = model.build_graph(d3.pos, d3.atomic_number, d3.cell)
+    g3 = d3.graph
+    model(d3)
+    assert d3.graph is g3
