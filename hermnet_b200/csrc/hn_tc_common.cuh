@@ -44,6 +44,27 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
+// Latency-critical wait (gather ring): plain try_wait loop without a suspend-time hint
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0, spins = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}\n"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (!ok && ++spins > (1u << 28)) {
+            printf("hermnet_b200: ring wait timed out (block %d thread %d bar 0x%x parity %u)\n", (int)blockIdx.x, (int)threadIdx.x, bar,
+                   parity);
+            __trap();
+        }
+    }
+}
+
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_proxy() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -60,6 +81,13 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
         "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
+}
+
+// 1-D bulk copy global -> shared (bytes % 16 == 0, both addresses 16-byte aligned), completion counted on an mbarrier
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
 }
 
 // K-major operand, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO = 64), LBO = 1, descriptor version 1
@@ -96,6 +124,18 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&r)[8]) {
                  : "r"(taddr));
 #pragma unroll
     for (int i = 0; i < 8; ++i) r[i] = __uint_as_float(v[i]);
+}
+// 4 consecutive TMEM columns of the calling thread's lane
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&r)[4]) {
+    uint32_t v[4];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r[i] = __uint_as_float(v[i]);
+}
+__device__ __forceinline__ void tmem_fence_regs(float (&r)[4]) {
+    asm volatile("" : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]));
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // Orders every later use of r[] after the preceding tmem_wait_ld (volatile asms keep their program order).
