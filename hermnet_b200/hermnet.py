@@ -163,9 +163,11 @@ class _HermNet(nn.Module):
             data.x, data.vec = x[g.inv_perm], vec[g.inv_perm]
         return energy
 
-    def forward_graph(self, pos, atomic_number, cell, g: RowGraph, halo=None):
+    def forward_graph(self, pos, atomic_number, cell, g: RowGraph, halo=None, atom_weight=None):
         """Hot path on a prebuilt ``RowGraph``: energies ``[num_graphs]`` plus final features (internal order).
-        ``halo`` (domain decomposition, ``parallel.Halo``) refreshes the ghost rows between layers."""
+        ``halo`` (domain decomposition, ``parallel.Halo``) refreshes the ghost rows between layers.
+        ``atom_weight [N]`` (caller's atom order): the readout sums ``w_i e_i`` instead of ``e_i`` -- partial energies of a
+        region, whose gradient only involves atoms within ``num_layers * rc`` of it (used by the cut-out parity check)."""
         F = self.hidden_channels
         fused = self._use_fused(pos)
         pos_i = pos[g.perm]
@@ -191,6 +193,8 @@ class _HermNet(nn.Module):
         tc = fused and self.tensor_core_linear
         h = self.out_energy[1](Fn.linear(x, self.out_energy[0].weight, self.out_energy[0].bias, tc))
         e_atom = self.out_energy[2](h)                                   # [N,1]   hermnet.py:129
+        if atom_weight is not None:
+            e_atom = e_atom * atom_weight.to(e_atom.dtype)[g.perm].unsqueeze(1)
         sb = g.seg_batch
         energy = Fn.segment_sum(e_atom, sb).squeeze(1)[: g.n_graphs]     # hermnet.py:130 (owned atoms only)
         if self.intensive and halo is None:

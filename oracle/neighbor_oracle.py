@@ -73,6 +73,34 @@ def neighbor_list_pbc(pos: np.ndarray, cell: np.ndarray, rc: float, centres=None
     return i[order], j[order], S[order]
 
 
+def neighbor_list_pbc_binned(pos: np.ndarray, cell: np.ndarray, rc: float):
+    """Same contract and exact test as ``neighbor_list_pbc`` at the cost of a production CPU list (what ASE's binning
+    achieves): candidates from a periodic k-d tree (scipy), then the ASE arithmetic on the original float32 positions.
+    Orthorhombic cells with every edge > 2 (rc + 1e-3) only (then an atom pair has at most one image in range).  Used by the
+    CPU-baseline leg of bench.py so that the reference arm is not charged for a brute-force list."""
+    from scipy.spatial import cKDTree
+    pos = np.ascontiguousarray(pos, dtype=np.float32)
+    cell = np.ascontiguousarray(cell, dtype=np.float32).reshape(3, 3)
+    c64 = cell.astype(np.float64)
+    L = np.diag(c64)
+    if np.abs(c64 - np.diag(L)).max() != 0.0 or (L <= 2 * (rc + 1e-3)).any():
+        raise ValueError("neighbor_list_pbc_binned: orthorhombic cell with edges > 2 rc required")
+    wrapped = np.mod(pos.astype(np.float64), L)
+    wrapped[wrapped >= L] = 0.0
+    tree = cKDTree(wrapped, boxsize=L)
+    pairs = tree.query_pairs(rc + 1e-3, output_type="ndarray").astype(np.int64)
+    ii = np.concatenate([pairs[:, 0], pairs[:, 1]])
+    jj = np.concatenate([pairs[:, 1], pairs[:, 0]])
+    d0 = (pos[jj] - pos[ii]).astype(np.float64)
+    S = -np.round(d0 / L).astype(np.int64)
+    dv = d0 + S.astype(np.float64) @ c64
+    dist = np.sqrt(dv[:, 0] * dv[:, 0] + dv[:, 1] * dv[:, 1] + dv[:, 2] * dv[:, 2])
+    keep = dist < rc
+    i, j, S = ii[keep], jj[keep], S[keep]
+    order = np.lexsort((S[:, 2], S[:, 1], S[:, 0], j, i))
+    return i[order], j[order], S[order]
+
+
 def radius_graph_nonpbc(pos: np.ndarray, rc: float, max_num_neighbors: int = 32, batch=None):
     """Return ``edge_index`` int64 ``[2,E]`` (row 0 = neighbour, row 1 = centre), sorted by (centre, neighbour)."""
     pos = np.ascontiguousarray(pos, dtype=np.float32)

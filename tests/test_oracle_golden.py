@@ -108,3 +108,18 @@ def test_oracle_symmetries_fp64():
         pp[a, k] += h; pm[a, k] -= h
         ep = O.hvnet_forward(sd, cfg, pp, Z, ei); em = O.hvnet_forward(sd, cfg, pm, Z, ei)
         assert abs(float(-(ep - em) / (2 * h)) - float(f0[a, k])) < 1e-6
+
+
+def test_binned_neighbour_list_equals_the_brute_force_oracle():
+    """The production-cost CPU list of bench.py's baseline leg == the brute-force restatement (same exact test)."""
+    from hermnet_b200 import synthetic
+    from oracle import neighbor_oracle as NO
+    pos, Z, cell = synthetic.cubic_lattice(6, 2.3, ("Li", "Al", "Si", "O"), None, 0.10, 4)
+    pos = pos + np.float32(7.5)          # atoms outside the cell: wrapped candidates, original-position test
+    a = NO.neighbor_list_pbc(pos, cell, 5.0)
+    b = NO.neighbor_list_pbc_binned(pos, cell, 5.0)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    case_pos, _, case_cell = synthetic.water_box(4, seed=0)
+    a = NO.neighbor_list_pbc(case_pos, case_cell, 5.0)
+    b = NO.neighbor_list_pbc_binned(case_pos, case_cell, 5.0)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
