@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--micro", type=int, default=4, help="C2: graphs per micro-batch")
     return ap.parse_args()
 
 
@@ -226,10 +227,142 @@ def parity_check(model, pos_d, Z_d, cell_d, graph, kind, cfg):
 
 
 # --------------------------------------------------------------------------------------------------------------
+def run_c2(args):
+    """``--workload C2`` (BASELINE.json configs[1]): HPNet L=3 F=128 K=128 on 32 synthetic 4 096-atom Li/Si/O cells, ONE
+    force-matching training step (example/dist_train.py:84-104: energy + force loss, forces with create_graph=True, double
+    backward, DDP gradient all-reduce, Adam) per bench step; the GLOBAL batch of 32 graphs is split over the ranks
+    (strong scaling), each rank runs its share in micro-batches with gradient accumulation."""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import torch.distributed as dist
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    import hermnet_b200 as H
+    from hermnet_b200 import ops, parallel, synthetic
+    GLOBAL = 32
+    assert GLOBAL % world == 0
+    n_side = max(2, int(round(16 * args.scale)))
+    (_, _, _), cfg = synthetic.config("C2", args.scale)
+    kind = cfg.pop("kind")
+    torch.manual_seed(1234)
+    model = getattr(H, kind)(**cfg).to(dev)
+    ddp = parallel.data_parallel(model, device_ids=[local], output_device=local) if world > 1 else model
+    ddp.train()
+    opt = torch.optim.Adam(ddp.parameters(), lr=3e-4)
+    mine = list(range(rank, GLOBAL, world))
+    host = []
+    gen = torch.Generator().manual_seed(99)
+    for gidx in mine:
+        pos, Z, cell = synthetic.cubic_lattice(n_side, 2.3, ("Li", "Si", "O"), (1 / 3, 1 / 6, 1 / 2), 0.10, 100 + gidx)
+        host.append(H.Data(pos=torch.from_numpy(pos).pin_memory(), atomic_number=torch.from_numpy(Z).pin_memory(),
+                           cell=torch.from_numpy(cell)[None].pin_memory(), y=torch.randn(1, generator=gen).pin_memory(),
+                           forces=(0.1 * torch.randn(pos.shape, generator=gen)).pin_memory()))
+    n_atoms_graph = int(host[0].pos.size(0))
+    micro = max(1, min(args.micro, len(host)))
+    resident = [H.Batch.from_data_list([d.to(dev) for d in host[i:i + micro]]) for i in range(0, len(host), micro)]
+
+    def step_resident():
+        return parallel.force_matching_step_microbatched(ddp, resident, opt, micro)
+
+    loss_h = torch.empty(1).pin_memory()
+
+    def step_e2e():
+        graphs = [d.to(dev, non_blocking=True) for d in host]
+        loss = parallel.force_matching_step_microbatched(ddp, graphs, opt, micro)
+        loss_h.copy_(loss.reshape(1), non_blocking=True)
+        torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ops.TIMERS = {}
+    ops.LAUNCHES["n"] = 0
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0.record()
+    for _ in range(args.steps):
+        step_resident()
+    t1.record()
+    barrier()
+    launches = ops.LAUNCHES["n"]
+    timers, ops.TIMERS = ops.TIMERS, None
+    ms = t0.elapsed_time(t1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_s = float("nan")
+    if args.e2e_steps > 0:
+        step_e2e()
+        barrier()
+        w0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            step_e2e()
+        barrier()
+        e2e_s = (time.perf_counter() - w0) / args.e2e_steps
+        if world > 1:
+            t = torch.tensor([e2e_s], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t)
+    n_par = sum(p.numel() for p in model.parameters())
+    if rank == 0:
+        kernels = {}
+        for name, evs in timers.items():
+            dur = [a.elapsed_time(b) for a, b in evs]
+            kernels[name] = {"launches": len(dur), "avg_ms": sum(dur) / len(dur), "share_of_step": sum(dur) / ms}
+        atoms = GLOBAL * n_atoms_graph
+        peak, peak_src = hbm_peak()
+        roof = None
+        if "gather_rows" in kernels:     # the hand-written kernels of the composite (double-backward) path are row gathers /
+            # segmented sums over [E, 3F] tensors: HBM-bound; algorithmic bytes = rows in + rows out, measured per launch
+            roof = {"kernel": "gather_rows", "bound": "hbm", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
+                    "traffic": None, "peak_source": peak_src,
+                    "note": "training runs the composite formulation (cuBLAS + torch elementwise + gather_rows / segment_sum); "
+                            "per-launch bytes vary with the tensor, see kernels{} for the time shares"}
+        bytes_in = sum(int(d[k].nbytes) for d in host for k in ("pos", "atomic_number", "cell", "y", "forces"))
+        line = {"metric": "atom-steps/s (training step)", "value": atoms * args.steps / (ms * 1e-3), "unit": "atom-steps/s",
+                "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"C2: {kind} L={cfg['num_layers']} F={cfg['hidden_channels']} K={cfg['num_rbf']} rc={cfg['rc']}, global "
+                                       f"batch {GLOBAL} x {n_atoms_graph}-atom Li/Si/O cells, force-matching training step (fwd, "
+                                       f"create_graph force grad, double backward, gradient all-reduce, Adam), {n_par} parameters"
+                                       + ("" if args.scale == 1.0 else f" [scale={args.scale}: NOT the BASELINE size]"),
+                           "parallelism": f"dp{world} (DDP, NCCL all-reduce), {len(mine)} graphs per rank in micro-batches of {micro}",
+                           "l2_policy": "per-step tensors exceed L2; no flush needed"},
+                "e2e": {"value": atoms / e2e_s, "unit": "atom-steps/s", "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": 4,
+                        "ms_per_step": 1e3 * e2e_s, "includes": "H2D of the local batch, collation, batched neighbour lists + row CSR, "
+                                                                  "training step, D2H of the loss"},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kernels}
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------------------------------
 def main():
     args = parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "C2":
+        return run_c2(args)
     if args.workload == "C5":      # 30 rows per atom: 20 GB tensors; avoid losing tens of GB to allocator fragmentation
         os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
 

@@ -18,7 +18,7 @@ from torch import Tensor
 
 from . import ops
 
-__all__ = ["neighbor_search", "transform", "Data", "Batch", "DataLoader"]
+__all__ = ["neighbor_search", "transform", "transform_batch", "Data", "Batch", "DataLoader"]
 
 
 def neighbor_search(pos: Tensor, rc: float, cell: Optional[Tensor] = None):
@@ -49,6 +49,36 @@ def transform(data, rc: float):
     else:
         data.edge_index, data.edge_shift = neighbor_search(data.pos, rc, data.cell)
     return data
+
+
+def transform_batch(batch, rc: float):
+    """Loader-side graph build for a COLLATED batch: one batched device neighbour search over all
+    graphs of the batch (every graph in its own cell) instead of ``transform`` per sample in ``__getitem__``
+    (data.py:58-67).  Attaches the same ``edge_index`` (and ``edge_shift``) the per-sample path followed by PyG collation
+    would give, as a set; edges are grouped by graph and sorted by ``edge_index[0]``."""
+    assert batch.pos is not None
+    dev = ops.compute_device(batch.pos)
+    p = batch.pos.detach().to(dev, torch.float32).contiguous()
+    n = p.size(0)
+    b = batch.get("batch")
+    b = torch.zeros(n, dtype=torch.long, device=dev) if b is None else b.to(dev).long()
+    n_graphs = int(b.max().item()) + 1 if n else 1
+    if n and not bool((b[1:] >= b[:-1]).all()):
+        raise ValueError("transform_batch: atoms must be grouped by graph (PyG collation order)")
+    gptr = torch.zeros(n_graphs + 1, dtype=torch.int32, device=dev)
+    gptr[1:] = torch.cumsum(torch.bincount(b, minlength=n_graphs), 0)
+    cell = batch.get("cell")
+    if cell is None:
+        rowptr, col, _ = ops.radius_graph(p, None, gptr, rc, None, 1, 32)
+        centre = ops.expand_rowptr(rowptr, col.numel())
+        batch.edge_index = torch.stack([col.long(), centre.long()]).to(batch.pos.device)
+        return batch
+    c = cell.detach().to(dev, torch.float32).reshape(-1, 3, 3).contiguous()
+    rowptr, col, shift = ops.radius_graph(p, c, gptr, rc, None, 1, 0)
+    centre = ops.expand_rowptr(rowptr, col.numel())
+    batch.edge_index = torch.stack([centre.long(), col.long()]).to(batch.pos.device)
+    batch.edge_shift = shift[:, :3].to(torch.float32).to(batch.pos.device)
+    return batch
 
 
 class Data:
@@ -161,9 +191,20 @@ class DataLoader:
     """Tiny stand-in for ``torch_geometric.loader.DataLoader`` (``batch_size``, ``shuffle``, ``sampler``)."""
 
     def __init__(self, dataset, batch_size: int = 1, shuffle: bool = False, sampler=None,
-                 collate_fn: Optional[Callable[[List[Data]], Data]] = None):
+                 collate_fn: Optional[Callable[[List[Data]], Data]] = None, rc: Optional[float] = None, device=None):
+        """``rc``: build the neighbour list of every collated batch with ONE batched device search (``transform_batch``)
+        -- for datasets that do not run ``transform`` per sample; ``device``: move the batch there first."""
         self.dataset, self.batch_size, self.shuffle, self.sampler = dataset, batch_size, shuffle, sampler
-        self.collate_fn = collate_fn or Batch.from_data_list
+        base = collate_fn or Batch.from_data_list
+        if rc is None and device is None:
+            self.collate_fn = base
+        else:
+            def collate(items):
+                b = base(items)
+                if device is not None:
+                    b = b.to(device)
+                return b if rc is None else transform_batch(b, rc)
+            self.collate_fn = collate
 
     def _indices(self):
         if self.sampler is not None:

@@ -238,3 +238,40 @@ def force_matching_step(model, data, optimizer, gamma: float = 0.8, trn_mean: fl
     loss.backward()
     optimizer.step()
     return loss.detach(), pred_e.detach(), pred_f.detach()
+
+
+def force_matching_step_microbatched(model, graphs, optimizer, micro: int = 4, gamma: float = 0.8, trn_mean: float = 0.0,
+                                     device=None):
+    """The same training step (example/dist_train.py:84-104) for a local batch given as a LIST of graphs, run in
+    micro-batches of ``micro`` graphs with gradient accumulation: the composite (double-backward) formulation keeps
+    ``[E,3F]`` tensors alive, a 32 x 4096-atom batch does not fit otherwise.  Under DDP only the last micro-batch
+    all-reduces (``no_sync`` on the others).  ``graphs``: ``Data`` objects or already collated micro-batches
+    (``Batch``; re-using them across steps re-uses their cached device graphs).  Losses are weighted so that the sum equals
+    the MSE over the whole local batch (energies per graph, forces per component)."""
+    import contextlib
+    from .data import Batch
+    optimizer.zero_grad()
+    batches = list(graphs) if isinstance(graphs[0], Batch) else \
+        [Batch.from_data_list(graphs[i:i + micro]) for i in range(0, len(graphs), micro)]
+    n_graphs = sum(int(b.get("num_graphs") or 1) for b in batches)
+    n_atoms = sum(int(b.pos.size(0)) for b in batches)
+    total = None
+    for i, data in enumerate(batches):
+        if device is not None and data.pos.device != torch.device(device):
+            data = data.to(device)
+        sync = i == len(batches) - 1 or not hasattr(model, "no_sync")
+        with (contextlib.nullcontext() if sync else model.no_sync()):
+            data.pos.requires_grad_(True)
+            pred_e = model(data)
+            w_e = float(pred_e.numel()) / n_graphs
+            w_f = float(data.pos.size(0)) / n_atoms
+            e_loss = torch.nn.functional.mse_loss(pred_e, data.y.reshape(-1) - trn_mean)
+            pred_f = -torch.autograd.grad(pred_e.sum(), data.pos, create_graph=True)[0]
+            f_loss = torch.nn.functional.mse_loss(pred_f, data.forces)
+            loss = (1 - gamma) * w_e * e_loss + gamma * w_f * f_loss
+            loss.backward()
+        total = loss.detach() if total is None else total + loss.detach()
+        data.pos.requires_grad_(False)
+        data.pos.grad = None
+    optimizer.step()
+    return total

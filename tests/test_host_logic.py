@@ -201,3 +201,29 @@ def test_auto_attached_graph_follows_the_current_inputs(emu):
     g3 = d3.graph
     model(d3)
     assert d3.graph is g3
+
+
+def test_loader_side_batched_graph_build_equals_per_sample_transform(emu):
+    """DataLoader(rc=...) builds the neighbour list of a collated batch in one batched search; the edge
+    set equals per-sample ``transform`` (data.py:27-35, 58-67) followed by PyG-style collation."""
+    from hermnet_b200 import synthetic
+    from oracle import neighbor_oracle as NO
+    samples = []
+    for seed in (100, 101, 102):
+        pos, Z, cell = synthetic.cubic_lattice(4 + seed % 2, 2.3, ("Li", "Si", "O"), (1 / 3, 1 / 6, 1 / 2), 0.10, seed)
+        samples.append(H.Data(pos=torch.from_numpy(pos), atomic_number=torch.from_numpy(Z), cell=torch.from_numpy(cell)[None],
+                              y=torch.tensor([float(seed)])))
+    per_sample = H.Batch.from_data_list([H.transform(H.Data(**dict(iter(d))), 5.0) for d in samples])
+    loader = H.DataLoader(samples, batch_size=3, rc=5.0)
+    (batched,) = list(loader)
+    a = NO.canonical_edges(per_sample.edge_index.numpy(), per_sample.edge_shift.numpy())
+    b = NO.canonical_edges(batched.edge_index.numpy(), batched.edge_shift.numpy())
+    assert a.shape[0] > 1000 and np.array_equal(a, b)
+    assert torch.equal(batched.batch, per_sample.batch) and batched.cell.shape == (3, 3, 3)
+    # and the model gives the same energies through either
+    case = util.load_case("batch3_mixed")
+    model, _ = util.make_model(case["kind"], case["cfg"], case["seed"])
+    d = util.make_data(case, with_edges=False, requires_grad=False)
+    d2 = H.transform_batch(util.make_data(case, with_edges=False, requires_grad=False), case["cfg"]["rc"])
+    assert d2.edge_index.size(1) == case["edges"].shape[0]
+    assert util.rel_err(model(d2).detach(), model(d).detach()) < 1e-6

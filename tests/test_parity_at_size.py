@@ -96,3 +96,18 @@ def test_domain_decomposition_equals_single_gpu_on_hardware():
         fh.write(r.stdout + "\n--- stderr ---\n" + r.stderr[-4000:])
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("OK") >= 3
+
+
+def test_ddp_gradients_equal_single_process_on_hardware():
+    """tests/ddp_gpu_check.py under torchrun (NCCL): gradient all-reduce of the training step == whole batch on one GPU."""
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(ROOT, "tests", "ddp_gpu_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "ddp_gpu_check.log"), "w") as fh:
+        fh.write(r.stdout + "\n--- stderr ---\n" + r.stderr[-4000:])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("OK") >= 2
