@@ -16,7 +16,7 @@ _LIB = None
 
 class EdgeParams(Structure):
     _fields_ = [("n_atoms", c_int32), ("n_rows", c_int32), ("n_modules", c_int32), ("hidden", c_int32),
-                ("num_rbf", c_int32), ("env_p", c_int32), ("inv_rc", c_float), ("coeff", c_float)]
+                ("num_rbf", c_int32), ("env_p", c_int32), ("inv_rc", c_float), ("coeff", c_float), ("variant", c_int32)]
 
 
 P = c_void_p  # every device pointer crosses the ABI as a plain address
@@ -44,8 +44,7 @@ SIGNATURES = {
     "hn_triplet_dots": (c_int32, [P, c_int32, P, P, P, c_int32, P, P]),
     "hn_edge_geom_fwd": (c_int32, [P, P, P, P, c_int32, P, P, c_float, c_int64, P, P]),
     "hn_edge_geom_bwd": (c_int32, [P, P, c_int32, P, P, c_int32, P, P, c_float, c_int64, c_int64, P, P, P]),
-    "hn_painn_edge_num_slices": (c_int32, [c_int32]),
-    "hn_painn_edge_set_variant": (c_int32, [c_int32]),
+    "hn_painn_edge_num_slices": (c_int32, [c_int32, c_int32]),
     "hn_painn_edge_fwd": (c_int32, [POINTER(EdgeParams)] + [P] * 13),
     "hn_painn_edge_bwd_dst": (c_int32, [POINTER(EdgeParams)] + [P] * 13 + [c_int64, P]),
     "hn_painn_edge_bwd_src": (c_int32, [POINTER(EdgeParams)] + [P] * 16),
@@ -73,7 +72,8 @@ SIGNATURES = {
     "hn_node_mid_bwd": (c_int32, [c_int64, c_int32, P, P, P, P, c_int64, P, P]),
     "hn_node_pre_bwd": (c_int32, [c_int64, c_int32, P, P, P, P, P, P, P]),
     "hn_gather_rows": (c_int32, [P, P, c_int64, c_int32, P, P]),
-    "hn_segment_sum": (c_int32, [P, P, P, c_int32, c_int32, P, P]),
+    "hn_segment_sum_workspace_bytes": (c_int64, [c_int32, c_int32]),
+    "hn_segment_sum": (c_int32, [P, P, P, c_int32, c_int32, P, P, c_int64, P]),
 }
 
 

@@ -18,7 +18,7 @@
 // same W rows in L1.
 // These row kernels are the fallback for F % 32 == 0 outside {64, 128, 256, 512} and the A/B partner of the tile-sweep
 // kernels of hn_edge_quad.cu, which share one band sweep between consecutive edges of a row and are the default
-// (hn_painn_edge_set_variant / HERMNET_B200_EDGE=row selects these).
+// (hn_edge_params.variant = 1 selects these).
 #include <cstdlib>
 #include <cstring>
 
@@ -435,17 +435,9 @@ int validate(const char *where, const hn_edge_params *p) {
     return 0;
 }
 
-// HERMNET_B200_EDGE=row forces the row-per-warp kernels of this file (A/B measurements, debugging); the default routes
-// F % 64 == 0 through the quad-tile kernels of hn_edge_quad.cu.
-int g_variant = -1;   // -1: not initialised, 0: auto (quad where supported), 1: row kernels only
-
-bool use_quad(const hn_edge_params *p) {
-    if (g_variant < 0) {
-        const char *e = getenv("HERMNET_B200_EDGE");
-        g_variant = (e != nullptr && strcmp(e, "row") == 0) ? 1 : 0;
-    }
-    return g_variant == 0 && hn::quad::supported(p);
-}
+// p->variant == 1 forces the row-per-warp kernels of this file (A/B measurements, debugging); the default (0) routes
+// F % 64 == 0 through the quad-tile kernels of hn_edge_quad.cu.  A per-call flag: the library keeps no selector state.
+bool use_quad(const hn_edge_params *p) { return p->variant == 0 && hn::quad::supported(p); }
 
 int row_slices(int hidden) {
     const int v = pick_vec(hidden);
@@ -454,15 +446,10 @@ int row_slices(int hidden) {
 
 }  // namespace
 
-extern "C" int hn_painn_edge_set_variant(int32_t variant) {
-    HN_REQUIRE(variant == 0 || variant == 1, "hn_painn_edge_set_variant", "variant must be 0 (auto) or 1 (row kernels)");
-    g_variant = variant;
-    return 0;
-}
-
-extern "C" int32_t hn_painn_edge_num_slices(int32_t hidden) {
+extern "C" int32_t hn_painn_edge_num_slices(int32_t hidden, int32_t variant) {
     hn_edge_params q = {};
     q.hidden = hidden;
+    q.variant = variant;
     if (row_slices(hidden) != 0 && use_quad(&q)) return hn::quad::bwd_dst_slices(hidden);
     return row_slices(hidden);
 }

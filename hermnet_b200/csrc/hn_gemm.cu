@@ -348,11 +348,8 @@ int launch(const float *A, int64_t M, int64_t K, int64_t lda, const float *Whi, 
     HN_REQUIRE(make_map(&tc, C, M, N, ldc, BM) == 0, where, "cuTensorMapEncodeTiled failed for C");
     if (C2 != nullptr) HN_REQUIRE(make_map(&tc2, C2, M, N, ldc2, BM) == 0, where, "cuTensorMapEncodeTiled failed for C2");
     else tc2 = tc;
-    static bool attr_set = false;
-    if (!attr_set) {
-        HN_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::kTotal), where);
-        attr_set = true;
-    }
+    // (a per-device attribute: set on every launch instead of remembering it in library state)
+    HN_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::kTotal), where);
     const long long tiles = (N / BN) * ((M + BM - 1) / BM);
     const int sms = hn::num_sms() > 0 ? hn::num_sms() : 148;
     dim3 grid((unsigned)(tiles < sms ? tiles : sms));

@@ -202,23 +202,32 @@ extern "C" int hn_gather_rows(const float *X, const int32_t *idx, int64_t n_out,
     return hn::check_launch("hn_gather_rows");
 }
 
+namespace {
+// chunks of the long-row path (few, possibly very long segments); 0: the short-row kernel needs no workspace
+int segment_sum_chunks(int32_t n_rows, int32_t C) {
+    if (!((long long)n_rows * C <= 4096 && C <= 64)) return 0;
+    const int sms = hn::num_sms() > 0 ? hn::num_sms() : 148;
+    const int total = n_rows * C;
+    int chunks = (sms * 4 + total - 1) / total;
+    return chunks < 1 ? 1 : (chunks > 256 ? 256 : chunks);
+}
+}  // namespace
+
+extern "C" int64_t hn_segment_sum_workspace_bytes(int32_t n_rows, int32_t C) {
+    if (n_rows <= 0 || C <= 0) return 0;
+    return (int64_t)sizeof(double) * n_rows * C * segment_sum_chunks(n_rows, C);
+}
+
 extern "C" int hn_segment_sum(const float *Y, const int32_t *rowptr, const int32_t *perm, int32_t n_rows, int32_t C,
-                              float *out, void *stream) {
+                              float *out, void *workspace, int64_t workspace_bytes, void *stream) {
     if (n_rows <= 0 || C <= 0) return 0;
     const int sms = hn::num_sms() > 0 ? hn::num_sms() : 148;
-    if ((long long)n_rows * C <= 4096 && C <= 64) {  // few, possibly very long segments
+    const int chunks = segment_sum_chunks(n_rows, C);
+    if (chunks > 0) {  // few, possibly very long segments: chunk partials in the CALLER's workspace (no library state)
         const int total = n_rows * C;
-        int chunks = (sms * 4 + total - 1) / total;
-        chunks = chunks < 1 ? 1 : (chunks > 256 ? 256 : chunks);
-        // chunk partials: a per-device scratch buffer of the library (8 MB, allocated on first use, never freed; calls
-        // on one device are expected to come from one stream at a time).  cudaMallocAsync here made every synchronised
-        // step re-grow the driver's pool (100+ ms stalls next to torch's caching allocator).
-        static double *scratch[64] = {nullptr};
-        int dev = 0;
-        HN_CUDA(cudaGetDevice(&dev), "hn_segment_sum");
-        HN_REQUIRE(dev >= 0 && dev < 64, "hn_segment_sum", "device ordinal out of range");
-        if (scratch[dev] == nullptr) HN_CUDA(cudaMalloc((void **)&scratch[dev], sizeof(double) * 4096 * 256), "hn_segment_sum");
-        double *partial = scratch[dev];
+        HN_REQUIRE(workspace != nullptr && workspace_bytes >= hn_segment_sum_workspace_bytes(n_rows, C), "hn_segment_sum",
+                   "workspace too small (hn_segment_sum_workspace_bytes)");
+        double *partial = (double *)workspace;
         dim3 grid(n_rows, C, chunks);
         segment_sum_long_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(Y, rowptr, perm, C, chunks, partial);
         segment_sum_finish_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partial, total, chunks, out);

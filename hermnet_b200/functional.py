@@ -166,12 +166,13 @@ def _split_cached(w: Tensor, transposed: bool):
     import weakref
     key = (id(w), transposed)
     hit = _SPLIT_CACHE.get(key)
-    if hit is not None and hit[0]() is w and hit[1] == w._version:
+    stamp = (w._version, w.data_ptr(), str(w.device))      # .data / .to() updates do not bump _version: also key on storage
+    if hit is not None and hit[0]() is w and hit[1] == stamp:
         return hit[2], hit[3]
     hi, lo = ops.split_tf32(w.detach().t().contiguous() if transposed else w.detach())
     if len(_SPLIT_CACHE) > 1024:
         _SPLIT_CACHE.clear()
-    _SPLIT_CACHE[key] = (weakref.ref(w), w._version, hi, lo)
+    _SPLIT_CACHE[key] = (weakref.ref(w), stamp, hi, lo)
     return hi, lo
 
 

@@ -141,8 +141,8 @@ class _HermNet(nn.Module):
         return g
 
     def _use_fused(self, pos) -> bool:
-        if self.edge_path == "fused":
-            return True
+        if self.edge_path == "fused":      # (bases / envelopes the kernels do not evaluate always take the composite path)
+            return self.radial_basis.fusable() and self.hidden_channels % 32 == 0 and pos.dtype == torch.float32
         if self.edge_path == "composite":
             return False
         return (not self.training) and self.radial_basis.fusable() and self.hidden_channels % 32 == 0 \

@@ -236,7 +236,7 @@ def edge_params(g, n_modules: int, hidden: int, num_rbf: int, env_p: int, rc: fl
 
 
 def edge_num_slices(hidden: int) -> int:
-    n = int(_lib.load().hn_painn_edge_num_slices(hidden))
+    n = int(_lib.load().hn_painn_edge_num_slices(hidden, 1 if EDGE_VARIANT["v"] == "row" else 0))
     if n <= 0:
         raise RuntimeError("hermnet_b200: hidden_channels must be a multiple of 32 for the fused edge kernels")
     return n
@@ -254,8 +254,12 @@ def edge_set_variant(variant: str) -> None:
     """'auto' / 'tc': tensor-core edge kernels where supported; 'quad': tile-sweep kernels; 'row': row-per-warp kernels."""
     if variant not in ("auto", "tc", "quad", "row"):
         raise ValueError(variant)
-    EDGE_VARIANT["v"] = variant
-    _lib.check(_lib.load().hn_painn_edge_set_variant(1 if variant == "row" else 0), "hn_painn_edge_set_variant")
+    EDGE_VARIANT["v"] = variant      # host-side preference only: every call stamps it into its hn_edge_params.variant
+
+
+def _stamp(p: EdgeParams) -> EdgeParams:
+    p.variant = 1 if EDGE_VARIANT["v"] == "row" else 0
+    return p
 
 
 def edge_use_tc(hidden: int, num_rbf: int) -> bool:
@@ -264,6 +268,7 @@ def edge_use_tc(hidden: int, num_rbf: int) -> bool:
 
 def painn_edge_fwd(p: EdgeParams, xh, vec, geom, g, Wt, bias, offset):
     lib = _lib.load()
+    _stamp(p)
     dev = _chk("painn_edge_fwd", xh, vec, geom, Wt, bias, offset)
     _f32("painn_edge_fwd", xh, vec, geom, Wt, bias, offset)
     F = p.hidden
@@ -278,6 +283,7 @@ def painn_edge_fwd(p: EdgeParams, xh, vec, geom, g, Wt, bias, offset):
 
 def painn_edge_bwd_dst(p: EdgeParams, xh, vec, geom, g, Wt, bias, offset, g_dx, g_dvec):
     lib = _lib.load()
+    _stamp(p)
     dev = _chk("painn_edge_bwd_dst", xh, vec, geom, Wt, bias, offset, g_dx, g_dvec)
     _f32("painn_edge_bwd_dst", xh, vec, geom, Wt, bias, offset, g_dx, g_dvec)
     g_geom = torch.empty((edge_num_slices(p.hidden), g.n_edges, 4), dtype=torch.float32, device=dev)
@@ -290,6 +296,7 @@ def painn_edge_bwd_dst(p: EdgeParams, xh, vec, geom, g, Wt, bias, offset, g_dx, 
 
 def painn_edge_bwd_src(p: EdgeParams, xh, vec, geom, g, Wt, bias, offset, g_dx, g_dvec):
     lib = _lib.load()
+    _stamp(p)
     dev = _chk("painn_edge_bwd_src", xh, vec, geom, Wt, bias, offset, g_dx, g_dvec)
     _f32("painn_edge_bwd_src", xh, vec, geom, Wt, bias, offset, g_dx, g_dvec)
     grad_xh = torch.zeros_like(xh)
@@ -341,7 +348,9 @@ def segment_sum(Y: Tensor, rowptr: Tensor, perm: Optional[Tensor], n_rows: int) 
     C = Y.size(1)
     out = torch.empty((n_rows, C), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev), _timed("segment_sum", dev):
-        _lib.check(lib.hn_segment_sum(_ptr(Y), _ptr(rowptr), _ptr(perm), n_rows, C, _ptr(out), _stream(dev)),
+        ws_bytes = int(lib.hn_segment_sum_workspace_bytes(n_rows, C))      # chunk partials of long rows: caller-owned
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev) if ws_bytes else None
+        _lib.check(lib.hn_segment_sum(_ptr(Y), _ptr(rowptr), _ptr(perm), n_rows, C, _ptr(out), _ptr(ws), ws_bytes, _stream(dev)),
                    "hn_segment_sum")
     return out
 

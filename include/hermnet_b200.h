@@ -133,13 +133,12 @@ typedef struct {
     int32_t env_p;        /* polynomial envelope exponent */
     float inv_rc;         /* 1/cutoff */
     float coeff;          /* Gaussian coefficient */
+    int32_t variant;      /* kernel family of hn_painn_edge_{fwd,bwd_dst,bwd_src}: 0 = auto (quad-tile kernels for F % 64 == 0,
+                             else row-per-warp), 1 = row-per-warp only (A/B measurements).  Per call: no library state. */
 } hn_edge_params;
 
-/* Planes of g_geom that hn_painn_edge_bwd_dst writes for this F (the caller sums them); 0 = unsupported F. */
-int32_t hn_painn_edge_num_slices(int32_t hidden);
-/* Kernel family behind hn_painn_edge_fwd / _bwd_dst / _bwd_src: 0 = auto (quad-tile kernels for F % 64 == 0, else
- * row-per-warp), 1 = row-per-warp only (A/B measurements; also selectable with HERMNET_B200_EDGE=row). */
-int hn_painn_edge_set_variant(int32_t variant);
+/* Planes of g_geom that hn_painn_edge_bwd_dst writes for this F and kernel family (the caller sums them); 0 = unsupported F. */
+int32_t hn_painn_edge_num_slices(int32_t hidden, int32_t variant);
 int hn_painn_edge_fwd(const hn_edge_params *p, const float *xh, const float *vec, const float *geom,
                       const int32_t *rowptr, const int32_t *col, const int32_t *row_mod, const int64_t *row_xoff,
                       const float *Wt, const float *bias, const float *offset, float *dx /*[R,F]*/,
@@ -239,8 +238,9 @@ int hn_tc_edge_bwd_src(const hn_edge_params *p, const hn_tc_plan *plan /*src-maj
  * decomposed path.
  * ------------------------------------------------------------------------------------------- */
 int hn_gather_rows(const float *X, const int32_t *idx, int64_t n_out, int32_t C, float *out, void *stream);
+int64_t hn_segment_sum_workspace_bytes(int32_t n_rows, int32_t C);   /* 0 when no workspace is needed */
 int hn_segment_sum(const float *Y, const int32_t *rowptr, const int32_t *perm, int32_t n_rows, int32_t C,
-                   float *out, void *stream);
+                   float *out, void *workspace, int64_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Node-side dense layers on the tcgen05 tensor cores (3xTF32 split, fp32-class accuracy):

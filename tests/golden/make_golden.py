@@ -81,6 +81,15 @@ def cases():
                                batch=np.concatenate(bs), seed=14,
                                cfg=dict(kind="HVNet", elems=["H", "O", "C"], rc=5.0, num_layers=2,
                                         hidden_channels=32, num_rbf=24))
+    # alternative radial bases / envelopes (rmnet.py:196-275) on a 24-atom water box, bar-sized K so that the
+    # Bernstein binomials stay in fp32 range
+    (pos, Z, cell), _ = synthetic.water_box(2, seed=31), None
+    for nm, rbf, env in (("a17_bessel_poly", {"name": "spherical_bessel"}, {"name": "polynomial", "exponent": 5}),
+                         ("a17_bernstein_exp", {"name": "bernstein"}, {"name": "exponential"}),
+                         ("a17_gauss_exp", {"name": "gaussian"}, {"name": "exponential"})):
+        out[nm] = dict(pos=pos, Z=Z, cell=cell[None], batch=np.zeros(len(Z), np.int64), seed=17,
+                       cfg=dict(kind="HVNet", elems=["H", "O"], rc=4.0, num_layers=2, hidden_channels=32, num_rbf=16,
+                                rbf=rbf, envelope=env))
     # builder-owned models (oracle only)
     (pos, Z, cell), _ = synthetic.water_box(2, seed=21), None
     out["water24_hpnet"] = dict(pos=pos, Z=Z, cell=cell[None], batch=np.zeros(len(Z), np.int64), seed=15,
@@ -111,8 +120,11 @@ def build_edges(H, case):
 
 def main():
     H = ref_shims.import_reference()
-    index = {}
+    only = set(sys.argv[1:])           # python make_golden.py [case ...]: (re)generate only these, keep the other index entries
+    index = json.load(open(os.path.join(OUT, "index.json"))) if only and os.path.exists(os.path.join(OUT, "index.json")) else {}
     for name, case in cases().items():
+        if only and name not in only:
+            continue
         cfg = case["cfg"]
         kind = cfg["kind"]
         mcfg = {k: v for k, v in cfg.items() if k != "kind"}
@@ -124,8 +136,9 @@ def main():
         if cell is not None:
             rec["cell"] = case["cell"]
         if kind == "HVNet":
+            extra = {k: mcfg[k] for k in ("rbf", "envelope") if k in mcfg}
             model = H.HVNet(elems=mcfg["elems"], rc=mcfg["rc"], num_layers=mcfg["num_layers"],
-                            hidden_channels=mcfg["hidden_channels"], num_rbf=mcfg["num_rbf"])
+                            hidden_channels=mcfg["hidden_channels"], num_rbf=mcfg["num_rbf"], **extra)
             model.load_state_dict(sd, strict=True)
             mk = lambda p, c: ref_shims.Data(pos=p, atomic_number=Z, edge_index=ei, batch=batch,
                                              **({} if c is None else dict(cell=c, edge_shift=es)))

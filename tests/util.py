@@ -33,8 +33,9 @@ def load_case(name):
 
 
 def make_model(kind, cfg, seed, device="cpu", **kw):
+    extra = {k: cfg[k] for k in ("rbf", "envelope") if k in cfg}
     model = getattr(H, kind)(elems=cfg["elems"], rc=cfg["rc"], num_layers=cfg["num_layers"],
-                             hidden_channels=cfg["hidden_channels"], num_rbf=cfg["num_rbf"], **kw)
+                             hidden_channels=cfg["hidden_channels"], num_rbf=cfg["num_rbf"], **extra, **kw)
     sd = O.make_state_dict(kind, cfg, seed)
     model.load_state_dict(sd, strict=True)
     return model.to(device).eval(), sd
