@@ -16,7 +16,7 @@ _LIB = None
 
 class EdgeParams(Structure):
     _fields_ = [("n_atoms", c_int32), ("n_rows", c_int32), ("n_modules", c_int32), ("hidden", c_int32),
-                ("num_rbf", c_int32), ("env_p", c_int32), ("inv_rc", c_float), ("coeff", c_float), ("variant", c_int32)]
+                ("num_rbf", c_int32), ("env_p", c_int32), ("inv_rc", c_float), ("coeff", c_float), ("variant", c_int32), ("flags", c_int32)]
 
 
 P = c_void_p  # every device pointer crosses the ABI as a plain address
@@ -25,7 +25,7 @@ P = c_void_p  # every device pointer crosses the ABI as a plain address
 class TcPlan(Structure):
     """``hn_tc_plan``: tile plan of the tensor-core edge kernels (device pointers)."""
     _fields_ = [("n_blocks", c_int32), ("n_tiles", c_int32), ("blk_info", c_void_p), ("blk_tile", c_void_p),
-                ("blk_xoff", c_void_p), ("tile_info", c_void_p), ("tile_win", c_void_p), ("erec", c_void_p), ("tile_geom", c_void_p)]
+                ("blk_xoff", c_void_p), ("tile_info", c_void_p), ("tile_win", c_void_p), ("erec", c_void_p), ("tile_geom", c_void_p), ("zero_row", c_void_p)]
 
 
 # name -> (restype, argtypes); must list EVERY symbol of include/hermnet_b200.h (checked by tests/test_abi.py)
@@ -59,7 +59,7 @@ SIGNATURES = {
     "hn_tc_plan_count": (c_int32, [P, P, P, c_int32, c_int32, P, P]),
     "hn_tc_plan_fill": (c_int32, [P, P, P, c_int32, c_int32, P, P, P]),
     "hn_tc_plan_finalize": (c_int32, [P, P, c_int32, c_int64, P, P, P, P, P]),
-    "hn_tc_tile_windows": (c_int32, [POINTER(TcPlan), P, c_float, c_int32, P]),
+    "hn_tc_tile_windows": (c_int32, [POINTER(TcPlan), P, P, c_float, c_int32, P]),
     "hn_tc_edge_fwd": (c_int32, [POINTER(EdgeParams), POINTER(TcPlan)] + [P] * 10 + [c_int64, P]),
     "hn_tc_edge_bwd_dst": (c_int32, [POINTER(EdgeParams), POINTER(TcPlan)] + [P] * 11),
     "hn_tc_edge_bwd_src": (c_int32, [POINTER(EdgeParams), POINTER(TcPlan)] + [P] * 12),

@@ -432,6 +432,7 @@ int validate(const char *where, const hn_edge_params *p) {
     HN_REQUIRE(p->num_rbf >= 2, where, "num_rbf must be >= 2");
     HN_REQUIRE(p->env_p >= 1, where, "envelope exponent must be >= 1");
     HN_REQUIRE(p->n_modules >= 1, where, "n_modules must be >= 1");
+    HN_REQUIRE(!(p->flags & 1), where, "Verlet-skin superset lists (flags bit 0) are only supported by the hn_tc_edge_* kernels");
     return 0;
 }
 

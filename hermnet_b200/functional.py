@@ -108,11 +108,14 @@ class _PaiNNEdge(Function):
         ctx.tc = ops.edge_use_tc(p.hidden, p.num_rbf) and g.n_edges > 0
         if ctx.tc:
             dst, _ = tileplan.plans_of(g, geom, p.inv_rc, p.num_rbf, want_src=False)
-            dst.update_windows(geom, p.inv_rc, p.num_rbf)
+            dst.update_windows(geom, p.inv_rc, p.num_rbf, getattr(p, "live", None))
             wsplit, wscale = ops.tc_split_weights(Wt)
             dx, dvec = ops.tc_edge_fwd(p, dst, xh, None if ctx.vec_null else vec, geom, wsplit, wscale, bias, offset, p.n_rows)
             ctx.wsplit = (wsplit, wscale)
         else:
+            if p.flags & 1:
+                raise RuntimeError("hermnet_b200: Verlet-skin graphs need the tensor-core edge kernels (hidden_channels == 128) "
+                                   "or the composite path (model.edge_path = 'composite')")
             dx, dvec = ops.painn_edge_fwd(p, xh, None if ctx.vec_null else vec, geom, g, Wt, bias, offset)
         ctx.g, ctx.p = g, p
         ctx.save_for_backward(xh, vec, geom, Wt, bias, offset)
@@ -132,14 +135,14 @@ class _PaiNNEdge(Function):
             dst, src = tileplan.plans_of(g, geom, p.inv_rc, p.num_rbf, want_src=tc_src and (need[0] or need[1]))
         if need[2]:
             if ctx.tc:
-                dst.update_windows(geom, p.inv_rc, p.num_rbf)
+                dst.update_windows(geom, p.inv_rc, p.num_rbf, getattr(p, "live", None))
                 parts = ops.tc_edge_bwd_dst(p, dst, xh, None if ctx.vec_null else vec, geom, wsplit, wscale, bias, offset, g_dx, g_dvec)
             else:
                 parts = ops.painn_edge_bwd_dst(p, xh, None if ctx.vec_null else vec, geom, g, Wt, bias, offset, g_dx, g_dvec)
             grad_geom = parts[0] if parts.size(0) == 1 else parts.sum(0)
         if need[0] or need[1]:
             if tc_src:
-                src.update_windows(geom, p.inv_rc, p.num_rbf)
+                src.update_windows(geom, p.inv_rc, p.num_rbf, getattr(p, "live", None))
                 grad_xh, grad_vec = ops.tc_edge_bwd_src(p, src, xh, vec, geom, wsplit, wscale, bias, offset, g_dx, g_dvec)
             else:
                 grad_xh, grad_vec = ops.painn_edge_bwd_src(p, xh, vec, geom, g, Wt, bias, offset, g_dx, g_dvec)
@@ -366,7 +369,7 @@ def edge_geometry_composite(pos: Tensor, cell: Optional[Tensor], g: RowGraph) ->
     return torch.cat([D / d[:, None], d[:, None]], dim=1)
 
 
-def painn_edge_composite_flat(xh, vec, geom, Wt, bias, radial_basis, g: RowGraph):
+def painn_edge_composite_flat(xh, vec, geom, Wt, bias, radial_basis, g: RowGraph, live_mask: Optional[Tensor] = None):
     """Same contract as ``painn_edge`` (``xh`` is the flat ``[rows, 3F]`` buffer of ``graph.xh_sources``) built from
     differentiable pieces; materialises per-edge tensors, so it is meant for training-size batches."""
     F3 = xh.size(1)
@@ -383,7 +386,10 @@ def painn_edge_composite_flat(xh, vec, geom, Wt, bias, radial_basis, g: RowGraph
     a, b, c = torch.split(P * phi, F, dim=-1)
     m_vec = V * (b * (1 / math.sqrt(3.0)))[:, None, :] + c[:, None, :] * geom[:, :3, None]
     m_vec = m_vec * (1 / math.sqrt(F))
-    live = (g.edge_mod >= 0).to(xh.dtype)[:, None]
+    live = g.edge_mod >= 0
+    if live_mask is not None:     # Verlet-skin superset list: dead entries are not edges of the reference
+        live = live & live_mask.bool()
+    live = live.to(xh.dtype)[:, None]
     dx = segment_sum(a * live, g.seg_dst)
     dvec = segment_sum((m_vec * live[:, :, None]).reshape(-1, F3), g.seg_dst).view(-1, 3, F)
     return dx, dvec

@@ -70,6 +70,8 @@ class RowGraph:
         self.own_count: List[int] = []  # per type: number of OWNED atoms (they come first inside the type slice);
         #                                 the rest of the slice are ghost atoms of a domain-decomposed system
         self.energy_index = None      # int32 [N]: graph id of owned atoms, n_graphs for ghosts
+        self.masked = False           # True: a Verlet-skin SUPERSET list (searched with rc + skin); the kernels drop d >= rc
+        self.list_rc = None           # search radius of the list
         self._lazy = {}
 
     # ---- lazily built segment views (only the differentiable / training formulation needs them) ----------
@@ -215,8 +217,18 @@ class GraphBuilder:
         return types_sorted.to(torch.int32).contiguous(), perm, inv, type_ptr
 
     def from_positions(self, pos: Tensor, Z: Tensor, cell: Optional[Tensor], batch: Optional[Tensor],
-                       max_neighbors: int = 0) -> RowGraph:
-        """Native path: cell-list radius graph on the device (replaces data.py:14-24 + utils.py:11-24)."""
+                       max_neighbors: int = 0, skin: float = 0.0) -> RowGraph:
+        """Native path: cell-list radius graph on the device (replaces data.py:14-24 + utils.py:11-24).
+        ``skin > 0``: Verlet list -- the search radius is ``rc + skin`` and the graph is marked ``masked``: it stays valid
+        while no atom has moved by more than ``skin / 2``, the edge kernels ignore entries with ``d >= rc``."""
+        g = self._from_positions(pos, Z, cell, batch, max_neighbors, float(skin))
+        g.masked, g.list_rc = skin > 0.0, self.rc + float(skin)
+        return g
+
+    def _from_positions(self, pos, Z, cell, batch, max_neighbors, skin) -> RowGraph:
+        rc_list = self.rc + skin
+        if skin > 0.0 and (cell is None or max_neighbors):
+            raise ValueError("Verlet-skin lists need a periodic cell (the non-periodic branch caps at 32 neighbours)")
         dev = pos.device
         n = pos.size(0)
         n_graphs = 1 if batch is None else (int(batch.max().item()) + 1 if n else 1)
@@ -227,7 +239,7 @@ class GraphBuilder:
             max_neighbors = 32   # torch_cluster default of the reference's non-periodic branch (data.py:16)
         if n_graphs == 1 and max_neighbors == 0:
             gptr = torch.tensor([0, n], dtype=torch.int32, device=dev)
-            rowptr, col, shift = ops.radius_graph(pos32[perm].contiguous(), cell32, gptr, self.rc,
+            rowptr, col, shift = ops.radius_graph(pos32[perm].contiguous(), cell32, gptr, rc_list,
                                                   types if self.n_groups > 1 else None, self.n_groups, 0)
             shift = -shift    # centre-row entry (j, S') is the reference edge (src=j, dst=centre, S=-S')
             return self._finish(n, n_graphs, rowptr, col, shift, types, perm, inv, type_ptr,
@@ -236,7 +248,7 @@ class GraphBuilder:
         b = torch.zeros(n, dtype=torch.long, device=dev) if batch is None else batch.long()
         gptr = torch.zeros(n_graphs + 1, dtype=torch.int32, device=dev)
         gptr[1:] = torch.cumsum(torch.bincount(b, minlength=n_graphs), 0)
-        rowptr, col, shift = ops.radius_graph(pos32.contiguous(), cell32, gptr, self.rc, None, 1, max_neighbors)
+        rowptr, col, shift = ops.radius_graph(pos32.contiguous(), cell32, gptr, rc_list, None, 1, max_neighbors)
         centre = ops.expand_rowptr(rowptr, col.numel())
         return self.from_coo(n, src=col.long(), dst=centre.long(), shift=-shift, Z=Z, batch=batch,
                              order=(types, perm, inv, type_ptr), pos=pos32, cell=cell32)

@@ -92,9 +92,11 @@ class _HermNet(nn.Module):
         pairs = pair_list(len(e))
         return [f"{e[a]}-{t}-{e[c]}" for t in e for (a, c) in pairs]
 
-    def build_graph(self, pos, atomic_number, cell=None, batch=None) -> RowGraph:
-        """Device neighbour search + row CSR for this model (replaces data.py:14-24 and utils.py:11-24)."""
-        return self.builder.from_positions(pos, atomic_number, cell, batch)
+    def build_graph(self, pos, atomic_number, cell=None, batch=None, skin: float = 0.0) -> RowGraph:
+        """Device neighbour search + row CSR for this model (replaces data.py:14-24 and utils.py:11-24).
+        ``skin > 0`` builds a Verlet list (radius ``rc + skin``) that MD drivers re-use while no atom has moved more than
+        ``skin / 2`` (plugin/md.py); edges that are at or beyond ``rc`` at evaluation time contribute nothing."""
+        return self.builder.from_positions(pos, atomic_number, cell, batch, skin=skin)
 
     @staticmethod
     def _input_key(data, names):
@@ -176,9 +178,12 @@ class _HermNet(nn.Module):
             geom = Fn.edge_geometry(pos_i, cell, g)
             gs = self.radial_basis.rbf
             p = ops.edge_params(g, g.n_modules, F, self.num_rbf, int(self.radial_basis.envelope.p), self.rc, gs.coeff)
+            p.flags = 1 if g.masked else 0
+            p.live = self._live_mask(pos_i, cell, g, geom) if g.masked else None
         else:
             geom = Fn.edge_geometry_composite(pos_i, cell, g)
             p = None
+            live_c = self._live_mask(pos_i, cell, g, geom) if g.masked else None
         x = self.embed(z_i)
         vec = torch.zeros((x.size(0), 3, F), dtype=x.dtype, device=x.device)
         ckpt = self._want_checkpoint(g, pos) if self.checkpoint_layers is None else bool(self.checkpoint_layers)
@@ -187,9 +192,10 @@ class _HermNet(nn.Module):
                 x, vec = halo.exchange(x, vec)
             if ckpt and torch.is_grad_enabled():
                 x, vec = torch_checkpoint(self._layer, conv, x, vec, geom, g, p, vec_zero=(li == 0),
-                                          z0=z_i if li == 0 else None, ckpt=True, use_reentrant=False)
+                                          z0=z_i if li == 0 else None, ckpt=True, live=None if fused else live_c, use_reentrant=False)
             else:
-                x, vec = self._layer(conv, x, vec, geom, g, p, vec_zero=(li == 0), z0=z_i if li == 0 else None)
+                x, vec = self._layer(conv, x, vec, geom, g, p, vec_zero=(li == 0), z0=z_i if li == 0 else None,
+                                     live=None if fused else live_c)
         tc = fused and self.tensor_core_linear
         h = self.out_energy[1](Fn.linear(x, self.out_energy[0].weight, self.out_energy[0].bias, tc))
         e_atom = self.out_energy[2](h)                                   # [N,1]   hermnet.py:129
@@ -203,7 +209,7 @@ class _HermNet(nn.Module):
         return energy, x, vec
 
     # ------------------------------------------------------------------------------------------------
-    def _layer(self, conv, x, vec, geom, g: RowGraph, p, vec_zero: bool = False, z0=None, ckpt: bool = False):
+    def _layer(self, conv, x, vec, geom, g: RowGraph, p, vec_zero: bool = False, z0=None, ckpt: bool = False, live=None):
         F = self.hidden_channels
         mods = list(conv.mods.values())
         # node side, part 1: projected source features of every sub-network, compact (graph.xh_sources)
@@ -224,7 +230,9 @@ class _HermNet(nn.Module):
                 uniq, g0 = self._layer0_tables(g, z0)
                 xs = self.embed(uniq)
                 xh = torch.cat([m.message_layer.node_features(xs) for m in mods], 0)
-                p0 = ops.EdgeParams(int(uniq.numel()), p.n_rows, p.n_modules, p.hidden, p.num_rbf, p.env_p, p.inv_rc, p.coeff)
+                p0 = ops.EdgeParams(int(uniq.numel()), p.n_rows, p.n_modules, p.hidden, p.num_rbf, p.env_p, p.inv_rc, p.coeff,
+                                    p.variant, p.flags)
+                p0.live = p.live
                 dx, dvec = Fn.painn_edge(xh, vec, geom, Wt, bias, self.radial_basis.rbf.offset, g0, p0, True)
             else:
                 xh = Fn.xproj_hv(x, [m.message_layer for m in mods], mods[0].message_layer.x_layernorm.eps)
@@ -259,7 +267,7 @@ class _HermNet(nn.Module):
         if p is not None:
             dx, dvec = Fn.painn_edge(xh, vec, geom, Wt, bias, self.radial_basis.rbf.offset, g, p, vec_zero)
         else:
-            dx, dvec = Fn.painn_edge_composite_flat(xh, vec, geom, Wt, bias, self.radial_basis, g)
+            dx, dvec = Fn.painn_edge_composite_flat(xh, vec, geom, Wt, bias, self.radial_basis, g, live)
         # node side, part 2: residual + update on the destination-element slices
         R = g.rows_per_atom
         dx = dx.view(-1, R, F)
@@ -321,6 +329,20 @@ class _HermNet(nn.Module):
         if n_unknown:
             pad(n_unknown)
         return torch.cat(xs, 0), torch.cat(vs, 0)
+
+    def _live_mask(self, pos_i, cell, g: RowGraph, geom):
+        """uint8 [E]: 1 where an entry of a Verlet-skin superset list is an edge of the reference NOW, i.e. where the
+        neighbour-list criterion ``|| pos_j - pos_i + S.cell || < rc`` (data.py:19-21, the physical distance) holds.  With
+        ``pbc_shift='physical'`` that is the model's own edge distance; with the reference's sign convention
+        the model distance of a boundary-crossing edge is a different number, so the criterion is evaluated separately."""
+        if g.sign < 0:
+            d = geom[:, 3].detach()
+        else:
+            from types import SimpleNamespace
+            phys = SimpleNamespace(atom_graph=g.atom_graph, edge_row=g.edge_row, rows_per_atom=g.rows_per_atom, col=g.col,
+                                   shift=g.shift, sign=-1.0, n_edges=g.n_edges)
+            d = ops.edge_geom_fwd(pos_i.detach().contiguous(), None if cell is None else cell.detach().contiguous(), phys)[:, 3]
+        return (d < self.rc).to(torch.uint8).contiguous()
 
     def _want_checkpoint(self, g: RowGraph, pos) -> bool:
         """Edge-side tensors a layer keeps for its backward pass: xh (+ its gradient), dx / dvec (+ gradients) and the

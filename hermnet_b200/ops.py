@@ -551,12 +551,14 @@ def tc_plan_finalize(order: Tensor, tile_start: Tensor, n_tiles: int, n_edges: i
     return erec, tile_info
 
 
-def tc_tile_windows(plan, geom: Tensor, inv_rc: float, num_rbf: int) -> None:
+def tc_tile_windows(plan, geom: Tensor, inv_rc: float, num_rbf: int, live: Optional[Tensor] = None) -> None:
     lib = _lib.load()
-    dev = _chk("tc_tile_windows", geom)
+    dev = _chk("tc_tile_windows", geom, live)
+    if live is not None and (live.dtype != torch.uint8 or live.numel() != geom.size(0)):
+        raise TypeError("hermnet_b200.tc_tile_windows: live must be uint8 [E]")
     with torch.cuda.device(dev), _timed("tc_tile_windows", dev):
-        _lib.check(lib.hn_tc_tile_windows(ctypes.byref(plan.cstruct()), _ptr(geom), float(inv_rc), int(num_rbf), _stream(dev)),
-                   "hn_tc_tile_windows")
+        _lib.check(lib.hn_tc_tile_windows(ctypes.byref(plan.cstruct()), _ptr(geom), _ptr(live), float(inv_rc), int(num_rbf),
+                                          _stream(dev)), "hn_tc_tile_windows")
 
 
 def tc_edge_fwd(p: EdgeParams, plan, xh, vec, geom, wsplit, wscale, bias, offset, n_rows: int, debug_phi: bool = False):

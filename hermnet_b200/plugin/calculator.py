@@ -62,7 +62,7 @@ class NNCalculator(Calculator):
     implemented_properties = ['energy', 'free_energy', 'forces', 'stress']
 
     def __init__(self, model: nn.Module, model_path: Optional[str], trn_mean: float, device_: str = 'cuda',
-                 ensemble: str = 'NVT', compat_stress: bool = False):
+                 ensemble: str = 'NVT', compat_stress: bool = False, skin: float = 0.0):
         super().__init__()
         self.device_ = device_
         device = torch.device(device_)
@@ -75,6 +75,10 @@ class NNCalculator(Calculator):
         self.trn_mean = trn_mean
         self.ensemble = ensemble
         self.compat_stress = compat_stress
+        # skin > 0: Verlet list re-used across calculate() calls while no atom moved more than skin / 2 (md.VerletGraph);
+        # 0 = a fresh neighbour list per call, as the reference does (calculator.py:42-57)
+        from .md import VerletGraph
+        self.verlet = VerletGraph(self.model, skin)
 
     def calculate(self, atoms, properties=None, system_changes=all_changes):
         super().calculate(atoms=atoms, properties=properties, system_changes=system_changes)
@@ -92,6 +96,8 @@ class NNCalculator(Calculator):
     def model_calc(self, data, device, pbc, ensemble='NVT'):
         """calculator.py:59-99: ``(float energy, ndarray[N,3] forces, ndarray[6] virial)``."""
         data = data.to(torch.device(device))
+        if pbc and self.verlet.skin > 0.0 and data.get("edge_index") is None:
+            data.graph = self.verlet.get(data.pos, data.atomic_number, data.get("cell"))
         data.pos.requires_grad_(True)
         npt = ensemble.lower() == 'npt'
         if npt and pbc:

@@ -75,19 +75,53 @@ def _kick(v, f, inv_m, dt):
     v.add_(f * inv_m, alpha=0.5 * dt)
 
 
-def velocity_verlet_device(model, numbers, positions, cell, velocities, steps: int, dt_fs: float = 0.5, device="cuda"):
-    """Device-resident MD: positions, velocities and forces never leave the GPU; per step only the
-    neighbour list / row CSR is rebuilt (device cell list) and one scalar energy may be read back by the caller."""
+class VerletGraph:
+    """Verlet-skin re-use of a model's device graph (neighbour list + row CSR + tile plans) across MD steps -- what the
+    reference rebuilds on the CPU on every call (plugin/ase_interface/calculator.py:42-57 -> build_graph).  The list is
+    searched with ``rc + skin`` and stays valid while no atom has moved by more than ``skin / 2`` since it was built; the
+    edge kernels drop the entries that are at or beyond ``rc`` at evaluation time, so energies / forces equal those of a
+    fresh list.  ``skin = 0``: rebuild every step (the reference's behaviour).  ``builds`` / ``reuses`` count what happened.
+    (Sub-networks are treated as active when the SUPERSET list has an edge for them -- hermnet.py:56-57 can only differ
+    for a sub-network whose every edge sits in the skin shell.)"""
+
+    def __init__(self, model, skin: float = 0.0):
+        self.model, self.skin = model, float(skin)
+        self.graph, self.ref_pos, self.ref_cell, self.ref_Z = None, None, None, None
+        self.builds = self.reuses = 0
+
+    def get(self, pos, Z, cell):
+        p = pos.detach()
+        if (self.graph is not None and self.skin > 0.0 and p.shape == self.ref_pos.shape and (Z is self.ref_Z or torch.equal(Z, self.ref_Z))
+                and ((cell is None) == (self.ref_cell is None)) and (cell is None or torch.equal(cell.detach(), self.ref_cell))):
+            moved = float((p - self.ref_pos).norm(dim=1).max())          # one scalar read-back per step
+            if moved < 0.5 * self.skin:
+                self.reuses += 1
+                return self.graph
+        self.graph = self.model.build_graph(p, Z, cell, None, skin=self.skin) if self.skin > 0.0 else \
+            self.model.build_graph(p, Z, cell, None)
+        self.ref_pos, self.ref_Z = p.clone(), Z
+        self.ref_cell = None if cell is None else cell.detach().clone()
+        self.builds += 1
+        return self.graph
+
+
+def velocity_verlet_device(model, numbers, positions, cell, velocities, steps: int, dt_fs: float = 0.5, device="cuda",
+                           skin: float = 0.0, stats: dict = None):
+    """Device-resident MD: positions, velocities and forces never leave the GPU; with ``skin > 0`` the
+    neighbour list / row CSR / tile plans are re-used across steps (``VerletGraph``), otherwise rebuilt per step (device
+    cell list).  ``stats`` (optional dict) receives the build / re-use counts."""
     dev = torch.device(device)
     Z = torch.as_tensor(np.asarray(numbers)).long().to(dev)
     pos = torch.as_tensor(np.asarray(positions), dtype=torch.float32).to(dev)
-    vel = torch.as_tensor(np.asarray(velocities), dtype=torch.float32).to(dev)
+    vel = torch.as_tensor(np.asarray(velocities), dtype=torch.float32).to(dev).clone()      # (never the caller's buffer)
     c = torch.as_tensor(np.asarray(cell), dtype=torch.float32).reshape(1, 3, 3).to(dev)
     masses = np.array([MASSES.get(int(z), 2.0 * int(z)) for z in np.asarray(numbers)])
     inv_m = torch.as_tensor(1.0 / (masses * AMU_A2_FS2_TO_EV), dtype=torch.float32).to(dev)[:, None]
+    vg = VerletGraph(model, skin)
 
     def forces(p):
         d = Data(pos=p.detach().requires_grad_(True), atomic_number=Z, cell=c)
+        d.graph = vg.get(d.pos, Z, c)
         e = model(d)
         (g,) = torch.autograd.grad(e.sum(), d.pos)
         return e.detach(), -g
@@ -100,4 +134,6 @@ def velocity_verlet_device(model, numbers, positions, cell, velocities, steps: i
         e, f = forces(pos)
         _kick(vel, f, inv_m, dt_fs)
         energies.append(e)
+    if stats is not None:
+        stats.update(builds=vg.builds, reuses=vg.reuses)
     return pos, vel, torch.cat(energies)

@@ -29,6 +29,7 @@ class TilePlan:
         self.n_blocks, self.n_tiles, self.has_inactive = n_blocks, n_tiles, has_inactive
         self.tile_win = torch.zeros((max(n_tiles, 1), 2), dtype=torch.int32, device=erec.device)
         self.tile_geom = torch.zeros((erec.size(0), 4), dtype=torch.float32, device=erec.device)
+        self.zero_row = torch.zeros(512, dtype=torch.float32, device=erec.device)     # staged for masked (d >= rc) edges
         self.win_key = None        # (data_ptr, version) of the geometry the windows were computed for
         self._c = None
 
@@ -36,7 +37,7 @@ class TilePlan:
         if self._c is None:
             self._c = TcPlan(self.n_blocks, self.n_tiles, self.blk_info.data_ptr(), self.blk_tile.data_ptr(),
                              self.blk_xoff.data_ptr(), self.tile_info.data_ptr(), self.tile_win.data_ptr(),
-                             self.erec.data_ptr(), self.tile_geom.data_ptr())
+                             self.erec.data_ptr(), self.tile_geom.data_ptr(), self.zero_row.data_ptr())
         return self._c
 
     def with_erec(self, erec: Tensor, blk_xoff: Tensor) -> "TilePlan":
@@ -47,12 +48,16 @@ class TilePlan:
         q._shared_with = self
         return q
 
-    def update_windows(self, geom: Tensor, inv_rc: float, num_rbf: int) -> None:
+    def update_windows(self, geom: Tensor, inv_rc: float, num_rbf: int, live: Optional[Tensor] = None) -> None:
+        """Windows + record-ordered geometry for THIS geometry tensor (``live``: uint8 [E], 0 = dead entry of a Verlet-skin
+        superset list).  Cached per tensor: the plan keeps a reference to the tensors it was computed for, so their addresses
+        cannot be recycled by the allocator while the cache entry is alive."""
         owner = getattr(self, "_shared_with", self)
-        key = (geom.data_ptr(), geom._version, tuple(geom.shape))
+        key = (geom.data_ptr(), geom._version, tuple(geom.shape), None if live is None else (live.data_ptr(), live._version))
         if owner.win_key != key:
-            ops.tc_tile_windows(owner, geom, inv_rc, num_rbf)
+            ops.tc_tile_windows(owner, geom, inv_rc, num_rbf, live)
             owner.win_key = key
+            owner._win_pin = (geom, live)
 
 
 def _tiles(order, kc, grp_ptr, n_groups, num_rbf, rec, grp_mod):

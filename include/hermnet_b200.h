@@ -135,6 +135,10 @@ typedef struct {
     float coeff;          /* Gaussian coefficient */
     int32_t variant;      /* kernel family of hn_painn_edge_{fwd,bwd_dst,bwd_src}: 0 = auto (quad-tile kernels for F % 64 == 0,
                              else row-per-warp), 1 = row-per-warp only (A/B measurements).  Per call: no library state. */
+    int32_t flags;        /* bit 0: the edge list is a Verlet-skin SUPERSET (built with rc + skin): the entries marked dead
+                             by hn_tc_tile_windows(live) must contribute nothing -- not even the filter bias (rmnet.py:55:
+                             the reference has no such edge).  Honoured by the hn_tc_edge_* kernels; the other families
+                             reject it. */
 } hn_edge_params;
 
 /* Planes of g_geom that hn_painn_edge_bwd_dst writes for this F and kernel family (the caller sums them); 0 = unsupported F. */
@@ -200,6 +204,7 @@ typedef struct {
     int32_t *tile_win;
     const int32_t *erec;
     float *tile_geom;          /* [E][4]: geometry of every record, written by hn_tc_tile_windows */
+    const float *zero_row;     /* >= 3F zeros (required when hn_edge_params.flags bit 0 is set, else may be NULL) */
 } hn_tc_plan;
 
 int32_t hn_tc_supported(int32_t hidden, int32_t num_rbf);
@@ -216,7 +221,9 @@ int hn_tc_plan_fill(const int32_t *order, const int32_t *kc, const int32_t *grp_
                     const int32_t *grp_tile /*[n_groups+1]*/, int32_t *tile_start /*[n_tiles]*/, void *stream);
 int hn_tc_plan_finalize(const int32_t *order, const int32_t *tile_start, int32_t n_tiles, int64_t n_edges,
                         const int32_t *rec /*[E][4]*/, const int32_t *tile_mod, int32_t *erec, int32_t *tile_info, void *stream);
-int hn_tc_tile_windows(const hn_tc_plan *plan, const float *geom, float inv_rc, int32_t num_rbf, void *stream);
+/* live: NULL, or uint8 [E] -- 0 marks an entry of a Verlet-skin superset list that is not an edge now (stored as -d in
+ * tile_geom; with hn_edge_params.flags bit 0 the edge kernels make it contribute nothing) */
+int hn_tc_tile_windows(const hn_tc_plan *plan, const float *geom, const uint8_t *live, float inv_rc, int32_t num_rbf, void *stream);
 int hn_tc_edge_fwd(const hn_edge_params *p, const hn_tc_plan *plan, const float *xh, const float *vec /*NULL: vec == 0*/,
                    const float *geom, const void *wsplit, const float *wscale, const float *bias, const float *offset,
                    float *dx, float *dvec, float *dbg /*NULL, or 2*E*3F + 14336 floats: phi | raw accumulators | first operand stage*/,

@@ -313,7 +313,7 @@ def tc_plan_finalize(order, tile_start, n_tiles, n_edges, rec, tile_mod):
     return erec, info
 
 
-def tc_tile_windows(plan, geom, inv_rc, num_rbf):
+def tc_tile_windows(plan, geom, inv_rc, num_rbf, live=None):
     K = num_rbf
     u = geom.detach()[:, 3] * inv_rc
     for t in range(plan.n_tiles):
@@ -327,7 +327,11 @@ def tc_tile_windows(plan, geom, inv_rc, num_rbf):
             hi = min(int(kc.max()) + 6, K - 1)
             nchunk = (hi - k0 + TC_KC) // TC_KC
         plan.tile_win[t, 0], plan.tile_win[t, 1] = k0, nchunk
-        plan.tile_geom[e0:e0 + cnt] = geom.detach()[plan.erec[e0:e0 + cnt, 3].long()]
+        eid = plan.erec[e0:e0 + cnt, 3].long()
+        tg = geom.detach()[eid].clone()
+        if live is not None:
+            tg[:, 3] = torch.where(live[eid].bool(), tg[:, 3], -tg[:, 3])
+        plan.tile_geom[e0:e0 + cnt] = tg
 
 
 def _tc_records(plan):
@@ -345,7 +349,8 @@ def _tc_records(plan):
 
 def _tc_phi(p, plan, geom, Wt, bias, offset, eid, mod, lo, hi, deriv=False):
     K = p.num_rbf
-    u = geom[:, 3] * p.inv_rc
+    dead = geom[:, 3] < 0                 # tc_tile_windows stores -d for the dead entries of a superset list
+    u = geom[:, 3].abs() * p.inv_rc
     pp = p.env_p
     a, b, c = -0.5 * (pp + 1) * (pp + 2), float(pp * (pp + 2)), -0.5 * pp * (pp + 1)
     env = 1 + a * u ** pp + b * u ** (pp + 1) + c * u ** (pp + 2)
@@ -355,11 +360,16 @@ def _tc_phi(p, plan, geom, Wt, bias, offset, eid, mod, lo, hi, deriv=False):
     inwin = (k >= lo[:, None]) & (k < hi[:, None]) & (u < 1)[:, None]
     val = torch.where(inwin, env[:, None] * gk, torch.zeros_like(gk))
     phi = torch.einsum("ek,ekc->ec", val, Wt[mod]) + bias[mod]
+    if getattr(p, "flags", 0) & 1:       # Verlet-skin superset list: dead entries contribute nothing
+        phi = torch.where(dead[:, None], torch.zeros_like(phi), phi)
     if not deriv:
         return phi, None
     denv = a * pp * u ** (pp - 1) + b * (pp + 1) * u ** pp + c * (pp + 2) * u ** (pp + 1)
     dval = torch.where(inwin, (denv[:, None] * gk + env[:, None] * gk * (2 * p.coeff * diff)) * p.inv_rc, torch.zeros_like(gk))
-    return phi, torch.einsum("ek,ekc->ec", dval, Wt[mod])
+    dphi = torch.einsum("ek,ekc->ec", dval, Wt[mod])
+    if getattr(p, "flags", 0) & 1:
+        dphi = torch.where(dead[:, None], torch.zeros_like(dphi), dphi)
+    return phi, dphi
 
 
 def tc_edge_fwd(p, plan, xh, vec, geom, wsplit, wscale, bias, offset, n_rows, debug_phi=False):

