@@ -13,7 +13,7 @@ from torch.utils.data import Sampler
 
 from . import ops
 
-__all__ = ["in_subgraph", "virial_calc", "DistributedEvalSampler"]
+__all__ = ["in_subgraph", "virial_calc", "DistributedEvalSampler", "save_checkpoint", "load_checkpoint"]
 
 
 def in_subgraph(data, nids: Any):
@@ -93,3 +93,28 @@ class DistributedEvalSampler(Sampler):
 
     def set_epoch(self, epoch):
         self.epoch = epoch
+
+
+def save_checkpoint(path, model, trn_mean, trn_e_loss=None, trn_f_loss=None, val_e_loss=None, val_f_loss=None):
+    """The checkpoint of the reference's hydra trainer (example/hydra-train/train.py:172-180): an ``OrderedDict`` with the
+    keys ``model`` (state_dict), ``trn_e_loss``, ``trn_f_loss``, ``val_e_loss``, ``val_f_loss``, ``trn_mean`` -- same keys, same
+    order, loadable by the reference's consumers."""
+    from collections import OrderedDict
+    infos = OrderedDict()
+    infos['model'] = model.state_dict()
+    infos['trn_e_loss'] = trn_e_loss
+    infos['trn_f_loss'] = trn_f_loss
+    infos['val_e_loss'] = val_e_loss
+    infos['val_f_loss'] = val_f_loss
+    infos['trn_mean'] = trn_mean
+    torch.save(infos, path)
+    return infos
+
+
+def load_checkpoint(path, map_location=None):
+    """``(state_dict, metadata)`` from either checkpoint flavour of the reference: a bare ``state_dict``
+    (example/dist_train.py:141, plugin/ase_interface/calculator.py:38) or the trainer's ``infos`` dict (train.py:172-180)."""
+    obj = torch.load(path, map_location=map_location)
+    if isinstance(obj, dict) and 'model' in obj and isinstance(obj['model'], dict):
+        return obj['model'], {k: v for k, v in obj.items() if k != 'model'}
+    return obj, {}

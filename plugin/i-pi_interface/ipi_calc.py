@@ -1,14 +1,23 @@
-"""i-PI driver entry point (reference: ``/root/reference/plugin/i-pi_interface/ipi_calc.py:5-18``).  The socket client
-is ASE's ``SocketClient`` (absent here, out of scope); the calculator handed to it is the B200-native one."""
-from hermnet_b200.plugin.calculator import NNCalculator
+"""i-PI driver entry point with the reference's signature (``/root/reference/plugin/i-pi_interface/ipi_calc.py:5-18``):
+``ipi_communicate(poscar, calc, host, port, mode)``.  With ASE installed the reference's own ``SocketClient`` is used;
+otherwise the pure-Python client of ``hermnet_b200.plugin.ipi`` speaks the same wire protocol."""
+from hermnet_b200.plugin import ipi, md
+from hermnet_b200.plugin.calculator import NNCalculator  # noqa: F401  (re-export, as the reference imports it here)
 
 
-def ipi_communicate(atoms, model, model_path, trn_mean, device='cuda', ensemble='NVT', port=31415, host='localhost'):
-    assert ensemble.lower() in ('nvt', 'npt', 'nve')
-    atoms.calc = NNCalculator(model, model_path, trn_mean, device_=device, ensemble=ensemble)
+def ipi_communicate(poscar: str, calc, host: str = 'localhost', port: int = 8888, mode: str = 'unix'):
+    assert mode in ['inet', 'unix']
     try:
         from ase.calculators.socketio import SocketClient
-    except Exception as exc:  # noqa: BLE001
-        raise RuntimeError("i-PI needs ase.calculators.socketio.SocketClient, which is not installed") from exc
-    client = SocketClient(host=host, port=port)
-    client.run(atoms, use_stress=ensemble.lower() == 'npt')
+        from ase.io.vasp import read_vasp
+        atoms = read_vasp(poscar)
+        atoms.calc = calc
+        client = SocketClient(host=host, port=port) if mode == 'inet' else SocketClient(unixsocket=host)
+        return client.run(atoms)
+    except ImportError:
+        symbols, pos, cell = ipi.read_poscar(poscar)
+        from hermnet_b200.symbols import atomic_numbers
+        atoms = md.SimpleAtoms([atomic_numbers[s] for s in symbols], pos, cell)
+        atoms.calc = calc
+        client = ipi.IPIClient(host=host, port=port) if mode == 'inet' else ipi.IPIClient(unixsocket=host)
+        return client.run(atoms, calc)
