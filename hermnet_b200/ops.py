@@ -340,6 +340,31 @@ def gather_rows(X: Tensor, idx: Tensor) -> Tensor:
     return out
 
 
+def halo_pack(x: Tensor, vec: Tensor, src_idx: Tensor, row_peer: Tensor, row_slot: Tensor, dst_base: Tensor) -> None:
+    """Rows ``[x | vec]`` of the atoms ``src_idx`` stored at ``dst_base[row_peer[i]] + row_slot[i] * 4F`` floats (device
+    addresses: peers' landing buffers over NVLink, or slices of a local send buffer)."""
+    lib = _lib.load()
+    dev = _chk("halo_pack", x, vec, src_idx, row_peer, row_slot, dst_base)
+    _f32("halo_pack", x, vec)
+    _i32("halo_pack", src_idx, row_peer, row_slot)
+    if dst_base.dtype != torch.int64:
+        raise TypeError("hermnet_b200.halo_pack: dst_base must be int64 device addresses")
+    with torch.cuda.device(dev), _timed("halo_pack", dev):
+        _lib.check(lib.hn_halo_pack(_ptr(x), _ptr(vec), _ptr(src_idx), _ptr(row_peer), _ptr(row_slot), _ptr(dst_base),
+                                    src_idx.numel(), x.size(1), _stream(dev)), "hn_halo_pack")
+
+
+def halo_unpack(buf: Tensor, dst_idx: Tensor, x: Tensor, vec: Tensor) -> None:
+    """Row ``i`` of ``buf [n, 4F]`` -> ``x[dst_idx[i]]``, ``vec[dst_idx[i]]`` (in place)."""
+    lib = _lib.load()
+    dev = _chk("halo_unpack", buf, dst_idx, x, vec)
+    _f32("halo_unpack", buf, x, vec)
+    _i32("halo_unpack", dst_idx)
+    with torch.cuda.device(dev), _timed("halo_unpack", dev):
+        _lib.check(lib.hn_halo_unpack(_ptr(buf), _ptr(dst_idx), dst_idx.numel(), x.size(1), _ptr(x), _ptr(vec), _stream(dev)),
+                   "hn_halo_unpack")
+
+
 def segment_sum(Y: Tensor, rowptr: Tensor, perm: Optional[Tensor], n_rows: int) -> Tensor:
     lib = _lib.load()
     dev = _chk("segment_sum", Y, rowptr, perm)

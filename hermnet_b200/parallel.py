@@ -76,25 +76,90 @@ def _all_to_all(send: Tensor, send_counts: List[int], recv_counts: List[int], gr
     return recv
 
 
+class PeerBuffers:
+    """Symmetric landing buffers of the halo exchange, mapped into every rank of the group (NVLink peer memory through
+    ``torch.distributed._symmetric_memory``): ``fwd [2, cap_ghost, W]`` receives ghost rows, ``bwd [2, cap_send, W]`` the
+    gradients flowing back to the owners; two slots each, used alternately (see ``_HaloExchange``).  Allocated once per
+    ``DomainDecomposition`` and re-used while the capacities suffice (every rank takes the same decision)."""
+
+    def __init__(self, cap_ghost: int, cap_send: int, width: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        self.cap_ghost, self.cap_send, self.width = cap_ghost, cap_send, width
+        grp = group if group is not None else dist.group.WORLD
+        self.fwd = symm.empty((2, max(cap_ghost, 1), width), dtype=torch.float32, device=device)
+        self.bwd = symm.empty((2, max(cap_send, 1), width), dtype=torch.float32, device=device)
+        self.h_fwd = symm.rendezvous(self.fwd, grp)
+        self.h_bwd = symm.rendezvous(self.bwd, grp)
+        world = dist.get_world_size(group)
+        row_bytes = width * 4
+        # device addresses of every peer's slots: [2, world]
+        self.fwd_ptrs = torch.tensor([[int(p) + s * max(cap_ghost, 1) * row_bytes for p in self.h_fwd.buffer_ptrs[:world]]
+                                      for s in range(2)], dtype=torch.int64, device=device)
+        self.bwd_ptrs = torch.tensor([[int(p) + s * max(cap_send, 1) * row_bytes for p in self.h_bwd.buffer_ptrs[:world]]
+                                      for s in range(2)], dtype=torch.int64, device=device)
+        self.n_fwd = self.n_bwd = 0       # exchanges issued so far (slot = count & 1)
+
+
 class Halo:
     """Send / receive lists of one rank.  ``send_idx``: local rows to pack, grouped by destination rank;
-    ``ghost_idx``: local ghost rows in the order the peers send them (grouped by owner rank)."""
+    ``ghost_idx``: local ghost rows in the order the peers send them (grouped by owner rank).
+
+    Transports of ``exchange`` (chosen once per halo):
+      * ``peer``  -- ``hn_halo_pack`` stores every row straight into the destination rank's ghost landing buffer over NVLink
+        peer memory, one device-side barrier, ``hn_halo_unpack`` moves the landed rows into the ghost rows; the backward
+        pass packs the ghost-row gradients into the OWNERS' buffers and reduces them there (``hn_segment_sum``);
+      * ``nccl``  -- the same kernels around one ``all_to_all_single`` (when symmetric memory cannot be set up);
+      * ``generic`` -- gather / point-to-point / index_copy on any backend (CPU tests with gloo)."""
 
     def __init__(self, send_idx: Tensor, send_counts: List[int], ghost_idx: Tensor, recv_counts: List[int],
-                 n_local: int, group=None):
+                 n_local: int, group=None, peer: Optional[PeerBuffers] = None):
         self.send_idx = send_idx.to(torch.int32).contiguous()
         self.ghost_idx = ghost_idx.long().contiguous()
+        self.ghost_idx32 = ghost_idx.to(torch.int32).contiguous()
         self.send_counts, self.recv_counts, self.group, self.n_local = send_counts, recv_counts, group, n_local
         self.seg_send = Segments.from_index(self.send_idx, n_local)     # adjoint of the pack gather
         self.bytes_per_exchange = 0
+        dev = self.send_idx.device
+        self.peer = peer
+        self.transport = "generic"
+        if dev.type == "cuda" and dist.is_initialized() and dist.get_backend(group) == "nccl":
+            self.transport = "peer" if peer is not None else "nccl"
+            rank, world = dist.get_rank(group), dist.get_world_size(group)
+            n_send, n_ghost = int(self.send_idx.numel()), int(self.ghost_idx.numel())
+            i32 = dict(dtype=torch.int32, device=dev)
+            if self.transport == "nccl":      # one local send buffer: "peer" 0, slot = position in the list
+                self.fwd_peer = torch.zeros(n_send, **i32)
+                self.fwd_slot = torch.arange(n_send, **i32)
+                self.bwd_peer = torch.zeros(n_ghost, **i32)
+                self.bwd_slot = torch.arange(n_ghost, **i32)
+            else:
+                # every rank's counts: S[r][p] rows r sends to p, R[r][p] rows r receives from p (= S[p][r]); device ops only
+                mine = torch.tensor([send_counts, recv_counts], dtype=torch.int64, device=dev)
+                allc = torch.empty((world, 2, world), dtype=torch.int64, device=dev)
+                dist.all_gather_into_tensor(allc, mine, group=group)
+                S, R = allc[:, 0], allc[:, 1]
+                recv_off = (torch.cumsum(R, 1) - R)[:, rank]      # [p]: where MY rows start in rank p's ghost zone
+                send_off = (torch.cumsum(S, 1) - S)[:, rank]      # [o]: where the rows for ME start in owner o's send list
+                ranks = torch.arange(world, device=dev)
+
+                def lists(counts, off):      # rows grouped by rank: (rank of every row, its slot in that rank's buffer)
+                    c = torch.tensor(counts, dtype=torch.int64, device=dev)
+                    start = torch.cumsum(c, 0) - c
+                    who = torch.repeat_interleave(ranks, c)
+                    slot = torch.arange(int(sum(counts)), device=dev) - start[who] + off[who]
+                    return who.to(torch.int32).contiguous(), slot.to(torch.int32).contiguous()
+                self.fwd_peer, self.fwd_slot = lists(send_counts, recv_off)      # my send list is grouped by destination rank
+                self.bwd_peer, self.bwd_slot = lists(recv_counts, send_off)      # my ghost list: by owner, in the owner's send order
 
     def exchange(self, x: Tensor, vec: Tensor) -> Tuple[Tensor, Tensor]:
         F = x.size(1)
-        feat = _HaloExchange.apply(torch.cat([x, vec.reshape(-1, 3 * F)], 1), self)
-        return feat[:, :F], feat[:, F:].reshape(-1, 3, F)
+        if self.transport == "generic":
+            feat = _HaloExchangeGeneric.apply(torch.cat([x, vec.reshape(-1, 3 * F)], 1), self)
+            return feat[:, :F], feat[:, F:].reshape(-1, 3, F)
+        return _HaloExchange.apply(x, vec, self)
 
 
-class _HaloExchange(Function):
+class _HaloExchangeGeneric(Function):
     @staticmethod
     def forward(ctx, feat: Tensor, halo: Halo):
         ctx.halo = halo
@@ -114,6 +179,65 @@ class _HaloExchange(Function):
         return g.index_fill(0, halo.ghost_idx, 0.0) + own, None
 
 
+class _HaloExchange(Function):
+    """Ghost rows of ``x`` / ``vec`` refreshed IN PLACE from their owners (the ghost rows of the inputs are padding written
+    by the node update).  Slot protocol of the peer transport: exchange k writes the peers' slot k & 1, then every rank
+    passes one device-side barrier, then reads its own slot; a rank can only reach exchange k + 2 (same slot) after barrier
+    k + 1, which every peer enters after its unpack k in stream order -- no second barrier is needed."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, vec: Tensor, halo: Halo):
+        ctx.halo = halo
+        ctx.mark_dirty(x, vec)
+        F = x.size(1)
+        n_send, n_ghost = int(halo.send_idx.numel()), int(halo.ghost_idx.numel())
+        halo.bytes_per_exchange = n_send * 4 * F * 4
+        v2 = vec.view(-1, 3 * F)
+        if halo.transport == "peer":
+            pb = halo.peer
+            slot = pb.n_fwd & 1
+            pb.n_fwd += 1
+            ops.halo_pack(x, v2, halo.send_idx, halo.fwd_peer, halo.fwd_slot, pb.fwd_ptrs[slot])
+            pb.h_fwd.barrier(channel=0)
+            ops.halo_unpack(pb.fwd[slot], halo.ghost_idx32, x, v2)
+        else:
+            send = torch.empty((n_send, 4 * F), dtype=x.dtype, device=x.device)
+            base = torch.tensor([send.data_ptr()], dtype=torch.int64, device=x.device)
+            ops.halo_pack(x, v2, halo.send_idx, halo.fwd_peer, halo.fwd_slot, base)
+            recv = torch.empty((n_ghost, 4 * F), dtype=x.dtype, device=x.device)
+            dist.all_to_all_single(recv, send, halo.recv_counts, halo.send_counts, group=halo.group)
+            ops.halo_unpack(recv, halo.ghost_idx32, x, v2)
+        return x, vec
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_x, g_vec):
+        halo = ctx.halo
+        g_x, g_vec = g_x.contiguous(), g_vec.contiguous()
+        F = g_x.size(1)
+        gv2 = g_vec.view(-1, 3 * F)
+        n_send, n_ghost = int(halo.send_idx.numel()), int(halo.ghost_idx.numel())
+        sg = halo.seg_send
+        if halo.transport == "peer":
+            pb = halo.peer
+            slot = pb.n_bwd & 1
+            pb.n_bwd += 1
+            ops.halo_pack(g_x, gv2, halo.ghost_idx32, halo.bwd_peer, halo.bwd_slot, pb.bwd_ptrs[slot])
+            pb.h_bwd.barrier(channel=0)
+            back = pb.bwd[slot][:n_send]
+        else:
+            send = torch.empty((n_ghost, 4 * F), dtype=g_x.dtype, device=g_x.device)
+            base = torch.tensor([send.data_ptr()], dtype=torch.int64, device=g_x.device)
+            ops.halo_pack(g_x, gv2, halo.ghost_idx32, halo.bwd_peer, halo.bwd_slot, base)
+            back = torch.empty((n_send, 4 * F), dtype=g_x.dtype, device=g_x.device)
+            dist.all_to_all_single(back, send, halo.send_counts, halo.recv_counts, group=halo.group)
+        own = ops.segment_sum(back.contiguous(), sg.rowptr, sg.perm, sg.n_rows)     # reverse accumulation on the owners
+        gx = g_x.index_fill(0, halo.ghost_idx, 0.0).add_(own[:, :F])
+        gv = g_vec.index_fill(0, halo.ghost_idx, 0.0)
+        gv.view(-1, 3 * F).add_(own[:, F:])
+        return gx, gv, None
+
+
 class DomainDecomposition:
     """Energy + forces of ONE periodic system spread over the ranks of ``group`` (inference path)."""
 
@@ -123,6 +247,11 @@ class DomainDecomposition:
         self.grid = _grid(self.world)
         self.graph: Optional[RowGraph] = None
         self.halo: Optional[Halo] = None
+        self.peer: Optional[PeerBuffers] = None
+        # HERMNET_B200_HALO=nccl forces the all-to-all transport (A/B measurements); default: peer memory when it can be set up
+        import os
+        self.want_peer = os.environ.get("HERMNET_B200_HALO", "peer") == "peer"
+        self.peer_error: Optional[str] = None
 
     # ------------------------------------------------------------------------------------------------------
     def _assign(self, pos: Tensor, cell: Tensor):
@@ -186,19 +315,42 @@ class DomainDecomposition:
         g2l[gid] = torch.arange(n_loc, device=dev)
         send_idx = g2l[asked]
         self.graph, self.ids = g, ids
-        self.halo = Halo(send_idx, send_counts, ghost_idx, recv_counts, n_loc, self.group)
         self.Z_local = Z[ids]                                          # local (pre-permutation) order, like pos[ids]
         self.cell = cell
         self.n_atoms, self.n_owned = N, n_own
-        stats = torch.tensor([n_own, g.n_edges, n_loc - n_own], dtype=torch.long, device=dev)
-        mx = stats.clone()
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=self.group)
+        stats = torch.tensor([n_own, g.n_edges, n_loc - n_own, int(send_idx.numel())], dtype=torch.long, device=dev)
+        both = torch.stack([stats, -stats])                            # one all-reduce: maxima, and minima as -max(-x)
         sm = stats.clone()
+        dist.all_reduce(both, op=dist.ReduceOp.MAX, group=self.group)
         dist.all_reduce(sm, op=dist.ReduceOp.SUM, group=self.group)
-        self.n_owned_max, self.local_edges_max, self.n_ghost_max = (int(v) for v in mx.tolist())
+        self.n_owned_max, self.local_edges_max, self.n_ghost_max, n_send_max = (int(v) for v in both[0].tolist())
         self.global_edges = int(sm[1])
+        self.halo = Halo(send_idx, send_counts, ghost_idx, recv_counts, n_loc, self.group,
+                         self._peer_buffers(self.n_ghost_max, n_send_max, dev))
         assert int(sm[0]) == N, "every atom must be owned by exactly one rank"
         return self
+
+    def _peer_buffers(self, ng: int, ns: int, dev) -> Optional[PeerBuffers]:
+        """Symmetric landing buffers (allocated once, grown when a new decomposition needs more rows); ``None`` when peer
+        memory is not available.  ``ng`` / ``ns`` are the all-reduced maxima of ghost / send rows, so every rank takes the same
+        decision without another collective; a failed set-up is shared with one."""
+        if not (self.want_peer and dev.type == "cuda" and dist.get_backend(self.group) == "nccl" and self.world > 1):
+            return None
+        width = 4 * self.model.hidden_channels
+        if self.peer is not None and self.peer.cap_ghost >= ng and self.peer.cap_send >= ns and self.peer.width == width:
+            return self.peer
+        ok = torch.ones(1, dtype=torch.long, device=dev)
+        peer = None
+        try:
+            peer = PeerBuffers(int(ng * 1.25) + 64, int(ns * 1.25) + 64, width, dev, self.group)
+        except Exception as exc:  # noqa: BLE001 -- no symmetric memory on this system: NCCL transport
+            self.peer_error = f"{type(exc).__name__}: {exc}"
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok) == 0:
+            self.want_peer, peer = False, None
+        self.peer = peer
+        return peer
 
     def energy_forces(self, pos: Tensor):
         """Total energy ``[1]`` and ``dE/dpos [N,3]`` (forces = minus that), identical on every rank."""

@@ -250,6 +250,21 @@ int hn_segment_sum(const float *Y, const int32_t *rowptr, const int32_t *perm, i
                    float *out, void *workspace, int64_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Halo exchange of the domain-decomposed path (no counterpart in the reference, whose only
+ * multi-GPU path is DDP, example/dist_train.py).  A landing-buffer row is [x (F) | vec (3F)] floats.
+ *   hn_halo_pack:   row i = features of atom src_idx[i]; stored at
+ *                   ((float *)dst_base[row_peer[i]]) + row_slot[i] * 4F -- dst_base[] holds device addresses: the PEERS'
+ *                   landing buffers mapped into this process (NVLink peer memory), or slices of one local send buffer
+ *                   (NCCL all-to-all fallback).
+ *   hn_halo_unpack: row i of buf -> x[dst_idx[i]], vec[dst_idx[i]] (the ghost rows).
+ * The backward pass calls the same pair with the lists swapped (ghost-row gradients into the owners' buffers, then
+ * hn_segment_sum): the reverse force accumulation.
+ * ------------------------------------------------------------------------------------------- */
+int hn_halo_pack(const float *x, const float *vec, const int32_t *src_idx, const int32_t *row_peer, const int32_t *row_slot,
+                 const uint64_t *dst_base, int64_t n_rows, int32_t hidden, void *stream);
+int hn_halo_unpack(const float *buf, const int32_t *dst_idx, int64_t n_rows, int32_t hidden, float *x, float *vec, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Node-side dense layers on the tcgen05 tensor cores (3xTF32 split, fp32-class accuracy):
  *   C[M,N] (row pitch ldc) = A[M,K] (row pitch lda) . W[N,K]^T + bias[N]   (bias may be NULL)
  * Replaces the cuBLAS fp32 GEMMs behind nn.Linear in HermNet/rmnet.py:40-49 (x_proj), :84-89

@@ -44,7 +44,7 @@ def main():
             good = de < 1e-5 and dg < 1e-4 * max(1.0, fs)
             ok &= good
             print(f"[dd_gpu_check] {kind} N={len(Z)} world={world} grid={dd.grid} owned<= {dd.n_owned_max} ghosts<= {dd.n_ghost_max} "
-                  f"edges={dd.global_edges}: rel dE={de:.2e} max|dG|={dg:.2e} (|G|max {fs:.2f}) {'OK' if good else 'FAIL'}", flush=True)
+                  f"edges={dd.global_edges} halo={dd.halo.transport}{'' if dd.peer_error is None else ' (' + dd.peer_error[:80] + ')'}: rel dE={de:.2e} max|dG|={dg:.2e} (|G|max {fs:.2f}) {'OK' if good else 'FAIL'}", flush=True)
         dist.barrier()
     dist.destroy_process_group()
     if rank == 0 and not ok:
