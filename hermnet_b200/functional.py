@@ -109,7 +109,7 @@ class _PaiNNEdge(Function):
         if ctx.tc:
             dst, _ = tileplan.plans_of(g, geom, p.inv_rc, p.num_rbf, want_src=False)
             dst.update_windows(geom, p.inv_rc, p.num_rbf, getattr(p, "live", None))
-            wsplit, wscale = ops.tc_split_weights(Wt)
+            wsplit, wscale = _tc_split_cached(Wt)
             dx, dvec = ops.tc_edge_fwd(p, dst, xh, None if ctx.vec_null else vec, geom, wsplit, wscale, bias, offset, p.n_rows)
             ctx.wsplit = (wsplit, wscale)
         else:
@@ -149,6 +149,27 @@ class _PaiNNEdge(Function):
         if need[3] or need[4]:
             grad_W, grad_b = ops.painn_edge_bwd_w(p, xh, vec, geom, g, offset, g_dx, g_dvec)
         return grad_xh, grad_vec, grad_geom, grad_W, grad_b, None, None, None, None
+
+
+_TC_SPLIT = {}
+
+
+def _tc_split_cached(Wt: Tensor):
+    """fp16 hi / lo split of the stacked filter weights for the tensor-core edge kernels, cached per live tensor object,
+    version and storage (the frozen-parameter path hands the same stacked tensor to every evaluation)."""
+    import weakref
+    key = id(Wt)
+    stamp = (Wt._version, Wt.data_ptr(), str(Wt.device), tuple(Wt.shape))
+    hit = _TC_SPLIT.get(key)
+    if hit is not None and hit[0]() is Wt and hit[1] == stamp:
+        return hit[2], hit[3]
+    wsplit, wscale = ops.tc_split_weights(Wt)
+    if Wt.requires_grad or Wt.grad_fn is not None:
+        return wsplit, wscale                       # a per-step tensor of the autograd graph: nothing to cache
+    if len(_TC_SPLIT) > 256:
+        _TC_SPLIT.clear()
+    _TC_SPLIT[key] = (weakref.ref(Wt), stamp, wsplit, wscale)
+    return wsplit, wscale
 
 
 def painn_edge(xh, vec, geom, Wt, bias, offset, g: RowGraph, p, vec_zero=False):
@@ -230,6 +251,31 @@ def _wsplit(w: Tensor, transposed: bool = False):
     return _split_cached(w, transposed)
 
 
+_XPROJ = {}
+
+
+def _xproj_folded(mods):
+    """First Linear of every sub-network with its LayerNorm affine folded in (W1.diag(gamma), b1 + W1.beta), concatenated
+    over the sub-networks, plus the TF32 hi / lo splits of it and of its transpose; cached per layer for frozen parameters
+    (the fused node path only runs with frozen parameters)."""
+    ps = [q for m in mods for q in (m.x_proj[0].weight, m.x_proj[0].bias, m.x_layernorm.weight, m.x_layernorm.bias)]
+    stamp = tuple((q._version, q.data_ptr(), str(q.device)) for q in ps)
+    key = id(mods[0])
+    hit = _XPROJ.get(key)
+    if hit is not None and hit[0] == stamp and hit[1]() is mods[0]:
+        return hit[2]
+    import weakref
+    w1 = torch.cat([m.x_proj[0].weight * m.x_layernorm.weight[None, :] for m in mods], 0).detach()
+    b1 = torch.cat([m.x_proj[0].bias + m.x_proj[0].weight @ m.x_layernorm.bias for m in mods]).detach().contiguous()
+    w1_hi, w1_lo = ops.split_tf32(w1)
+    w1t_hi, w1t_lo = ops.split_tf32(w1.t().contiguous())
+    out = (w1, b1, w1_hi, w1_lo, w1t_hi, w1t_lo)
+    if len(_XPROJ) > 256:
+        _XPROJ.clear()
+    _XPROJ[key] = (stamp, weakref.ref(mods[0]), out)
+    return out
+
+
 class _XProjHV(Function):
     """``xh[m] = x_proj_m(LayerNorm_m(x))`` for every sub-network m of an HVNet layer (rmnet.py:52 run per element,
     hermnet.py:51-59), written straight into the flat ``[M*N, 3F]`` buffer the edge kernel reads.  The normalisation is
@@ -241,9 +287,7 @@ class _XProjHV(Function):
         N, F = x.shape
         M = len(mods)
         xhat, mean, rstd = torch.native_layer_norm(x, (F,), None, None, eps)
-        w1 = torch.cat([m.x_proj[0].weight * m.x_layernorm.weight[None, :] for m in mods], 0).detach()
-        b1 = torch.cat([m.x_proj[0].bias + m.x_proj[0].weight @ m.x_layernorm.bias for m in mods]).detach().contiguous()
-        w1_hi, w1_lo = ops.split_tf32(w1)
+        w1, b1, w1_hi, w1_lo, w1t_hi, w1t_lo = _xproj_folded(mods)
         hpre = torch.empty((N, M * F), dtype=x.dtype, device=x.device)
         h = torch.empty_like(hpre)
         ops.gemm_tf32x3_ex(xhat, w1_hi, w1_lo, b1, out=h, mode=1, out2=hpre)
@@ -251,7 +295,7 @@ class _XProjHV(Function):
         for m, mod in enumerate(mods):
             hi, lo = _wsplit(mod.x_proj[2].weight)
             ops.gemm_tf32x3_ex(h[:, m * F:(m + 1) * F], hi, lo, mod.x_proj[2].bias.detach(), out=xh[m * N:(m + 1) * N])
-        ctx.mods, ctx.w1 = mods, w1
+        ctx.mods, ctx.w1t = mods, (w1t_hi, w1t_lo)
         ctx.save_for_backward(x, mean, rstd, hpre)
         return xh
 
@@ -267,7 +311,7 @@ class _XProjHV(Function):
             hi, lo = _wsplit(mod.x_proj[2].weight, True)                      # [F, 3F]: g_h = g_xh . W2
             ops.gemm_tf32x3_ex(g_xh[m * N:(m + 1) * N], hi, lo, None, out=g_pre[:, m * F:(m + 1) * F], mode=2,
                                aux=hpre[:, m * F:(m + 1) * F])
-        hi, lo = ops.split_tf32(ctx.w1.t().contiguous())                      # [F, M*F]
+        hi, lo = ctx.w1t                                                      # [F, M*F]
         g_xhat = ops.gemm_tf32x3_ex(g_pre, hi, lo, None)
         g_x = torch.ops.aten.native_layer_norm_backward(g_xhat, x, [F], mean, rstd, None, None, [True, False, False])[0]
         return g_x, None, None

@@ -218,8 +218,7 @@ class _HermNet(nn.Module):
         # reference runs a full LayerNorm pass over all N rows per sub-network (rmnet.py:52).
         if self._fused_node_path(conv, p, g):
             # frozen HVNet parameters on the fused path: hand-written forward/backward for the whole node side
-            Wt = torch.stack([m.message_layer.rbf_proj.weight.t() for m in mods])
-            bias = torch.stack([m.message_layer.rbf_proj.bias for m in mods])
+            Wt, bias = self._frozen_filter(conv, mods)
             if vec_zero and z0 is not None and not self.embed.weight.requires_grad:
                 # first layer: x = Embedding[Z] (hermnet.py:123), so the projected source features only depend on the
                 # ELEMENT of the source.  The edge kernels read a [M * n_elements, 3F] table (L1-resident) through an
@@ -329,6 +328,20 @@ class _HermNet(nn.Module):
         if n_unknown:
             pad(n_unknown)
         return torch.cat(xs, 0), torch.cat(vs, 0)
+
+    def _frozen_filter(self, conv, mods):
+        """Stacked ``rbf_proj`` weights ``Wt [M,K,3F]`` / biases ``[M,3F]`` of a layer whose parameters are frozen, cached per
+        layer (identity, version and storage of every parameter are checked) -- a fresh stack per evaluation costs host time
+        that shows once a rank's kernels take tens of microseconds (8-GPU domain decomposition)."""
+        ps = [q for m in mods for q in (m.message_layer.rbf_proj.weight, m.message_layer.rbf_proj.bias)]
+        stamp = tuple((q._version, q.data_ptr(), str(q.device)) for q in ps)
+        hit = getattr(conv, "_hb_filter", None)
+        if hit is None or hit[0] != stamp:
+            Wt = torch.stack([m.message_layer.rbf_proj.weight.detach().t() for m in mods]).contiguous()
+            bias = torch.stack([m.message_layer.rbf_proj.bias.detach() for m in mods]).contiguous()
+            hit = (stamp, Wt, bias)
+            object.__setattr__(conv, "_hb_filter", hit)
+        return hit[1], hit[2]
 
     def _live_mask(self, pos_i, cell, g: RowGraph, geom):
         """uint8 [E]: 1 where an entry of a Verlet-skin superset list is an edge of the reference NOW, i.e. where the
