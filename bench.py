@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--micro", type=int, default=4, help="C2: graphs per micro-batch")
+    ap.add_argument("--cuda-graph", type=int, default=1, help="C4: replay the resident step as ONE captured CUDA graph (0: eager launches)")
     return ap.parse_args()
 
 
@@ -217,8 +218,9 @@ def parity_check(model, pos_d, Z_d, cell_d, graph, kind, cfg):
     the oracle is the checker here, never the thing measured."""
     from tests import cutout
     sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
-    out = cutout.cutout_parity(model, sd, dict(cfg), pos_d, Z_d, cell_d, r_in=4.0, graph=graph)
-    return {"rel_dE": out["rel_dE"], "max_dF": max(out["max_dF"], out.get("max_dF_interior", 0.0)), "n_checked": out["n_cutout"],
+    out = cutout.cutout_parity(model, sd, dict(cfg), pos_d, Z_d, cell_d, r_in=4.0, graph=graph, fp64_reference=True)
+    return {"rel_dE": out["rel_dE"], "rel_dE_vs_fp64_oracle": out["rel_dE_vs_fp64"], "fp32_oracle_vs_fp64_oracle": out["oracle_fp32_vs_fp64"],
+            "E_region_eV": out["E_region"], "max_dF": max(out["max_dF"], out.get("max_dF_interior", 0.0)), "n_checked": out["n_cutout"],
             "n_interior_true_forces": out["n_interior"], "max_dF_interior": out.get("max_dF_interior"),
             "method": f"oracle on the {out['n_cutout']}-atom cut-out (r = {out['r_cutout']:.0f} A) of the full system; E of the "
                       f"{out['n_region']}-atom region, dE/dpos over the cut-out, true forces of the interior atoms",
@@ -350,10 +352,8 @@ def run_c2(args):
                         "ms_per_step": 1e3 * e2e_s, "includes": "H2D of the local batch, collation, batched neighbour lists + row CSR, "
                                                                   "training step, D2H of the loss"},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "kernels": kernels}
-        sys.stdout.flush()
-        os.write(real_stdout, (json.dumps(line) + "\n").encode())
-    if world > 1:
-        dist.destroy_process_group()
+        _finish(world, real_stdout, line)
+    _finish(world, None, None)
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -413,13 +413,14 @@ def main():
         engine.build(pos_d, Z_d, cell_d)
         n_edges = engine.global_edges
 
-    def step_resident():
+    def step_resident(pos_in=None):
+        src = pos_d if pos_in is None else pos_in
         if engine is None:
-            p = pos_d.detach().requires_grad_(True)
+            p = src.detach().requires_grad_(True)
             e, _, _ = model.forward_graph(p, Z_d, cell_d, graph)
             (g,) = torch.autograd.grad(e.sum(), p)
-            return e, g
-        return engine.energy_forces(pos_d)
+            return e.detach(), g
+        return engine.energy_forces(src)
 
     def step_e2e():
         p = pos_h.to(dev, non_blocking=True)
@@ -445,25 +446,54 @@ def main():
     for _ in range(max(3, args.warmup)):
         step_resident()
     barrier()
+
+    def timed(step_fn, collect):
+        """K steps bracketed by barrier + synchronize, CUDA events, max over ranks; ``collect``: per-kernel events."""
+        if collect:
+            ops.TIMERS = {}
+        ops.LAUNCHES["n"] = 0
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        a.record()
+        for _ in range(args.steps):
+            step_fn()
+        b.record()
+        barrier()
+        n_launch = ops.LAUNCHES["n"]
+        tm, ops.TIMERS = ops.TIMERS, None
+        t_ms = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([t_ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_ms = float(t)
+        return t_ms, n_launch, tm
+
+    # eager pass: every launch individually, CUDA events around each kernel (the per-kernel table / roofline come from here)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ops.TIMERS = {}
-    ops.LAUNCHES["n"] = 0
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t0.record()
-    for _ in range(args.steps):
-        step_resident()
-    t1.record()
-    barrier()
-    launches = ops.LAUNCHES["n"]
-    timers, ops.TIMERS = ops.TIMERS, None
-    ms = t0.elapsed_time(t1)
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t)
+    ms_eager, launches, timers = timed(step_resident, True)
+    # graphed pass: the same step (forward_graph + autograd.grad [+ halo exchange and all-reduces]) captured ONCE and replayed
+    graphed, graph_note = None, "eager launches"
+    if args.cuda_graph:
+        try:
+            from hermnet_b200.graphed import GraphedForces
+            graphed = GraphedForces(step_resident, pos_d)
+            for _ in range(3):
+                graphed()
+            ok = torch.ones(1, device=dev)
+        except Exception as exc:  # noqa: BLE001 -- capture is an optimisation: fall back to eager launches, say why
+            graphed, graph_note = None, f"eager launches (capture failed: {type(exc).__name__}: {str(exc)[:120]})"
+            ok = torch.zeros(1, device=dev)
+        if world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok) == 0:
+            graphed = None
+    if graphed is not None:
+        ms, _, _ = timed(graphed, False)
+        graph_note = "one captured CUDA graph per step (forward + backward [+ halo exchange, all-reduces]) replayed"
+    else:
+        ms = ms_eager
     clocks = sampler.stop() if rank == 0 else None
     ms_per_step = ms / args.steps
     value = N * args.steps / (ms * 1e-3)
@@ -485,15 +515,13 @@ def main():
         e2e_s = float(t)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        _finish(world, None, None)
 
     # ---- per-kernel device times (CUDA events recorded around every launch inside the timed region) ------------
     kernels = {}
     for name, evs in timers.items():
         dur = [a.elapsed_time(b) for a, b in evs]
-        kernels[name] = {"launches": len(dur), "avg_ms": sum(dur) / len(dur), "share_of_step": sum(dur) / ms}
+        kernels[name] = {"launches": len(dur), "avg_ms": sum(dur) / len(dur), "share_of_step": sum(dur) / ms_eager}
     peak, peak_src = hbm_peak()
     n_loc = N if engine is None else engine.n_owned_max
     e_loc = n_edges if engine is None else engine.local_edges_max
@@ -523,7 +551,9 @@ def main():
                                f"{N}-atom {'/'.join(cfg['elems'])} periodic box (E={n_edges} directed edges), energy + forces, "
                                f"parameters frozen" + ("" if args.scale == 1.0 else f" [scale={args.scale}: NOT the BASELINE size]"),
                    "parallelism": "single GPU" if world == 1 else f"spatial domain decomposition over {world} GPUs, per-layer halo exchange",
-                   "l2_policy": "inputs exceed L2 (feature tensors are GBs); no flush needed"},
+                   "l2_policy": "inputs exceed L2 (feature tensors are GBs); no flush needed",
+                   "launch_mode": graph_note},
+        "ms_per_step_eager": ms_eager / args.steps,
         "e2e": {"value": N / e2e_s, "unit": "atom-steps/s", "h2d_bytes_per_step": int(pos_h.nbytes + Z_h.nbytes + cell_h.nbytes),
                 "d2h_bytes_per_step": int(f_h.nbytes + e_h.nbytes), "ms_per_step": 1e3 * e2e_s,
                 "includes": "H2D, neighbour-list + row-CSR build, forward, backward, D2H of forces and energy"},
@@ -533,10 +563,21 @@ def main():
         line["parity"] = parity_check(model, pos_d, Z_d, cell_d, graph, kind, cfg)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(dict(cfg, kind=kind))
+    _finish(world, real_stdout, line)
+
+
+def _finish(world, real_stdout, line):
+    """Print the line (rank 0) and leave WITHOUT tearing down NCCL / symmetric memory / captured graphs: destroying a
+    process group whose collectives live in a CUDA graph can block, and the process is done anyway."""
     sys.stdout.flush()
-    os.write(real_stdout, (json.dumps(line) + "\n").encode())
-    if world > 1:
-        dist.destroy_process_group()
+    sys.stderr.flush()
+    if line is not None:
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+    try:
+        torch.cuda.synchronize()
+    except Exception:  # noqa: BLE001
+        pass
+    os._exit(0)
 
 
 if __name__ == "__main__":

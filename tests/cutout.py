@@ -30,7 +30,7 @@ def min_image_dist(pos: torch.Tensor, cell: torch.Tensor, centre: int) -> torch.
 
 
 def cutout_parity(model, sd, cfg, pos, Z, cell, r_in: float = 4.0, centre: int | None = None, graph=None,
-                  check_full_forces: bool = True, r_region: float | None = None):
+                  check_full_forces: bool = True, r_region: float | None = None, fp64_reference: bool = False):
     """Returns a dict with ``rel_dE`` (partial energy), ``max_dF`` (gradient of the partial energy over the whole
     cut-out, eV/A), ``max_dF_interior`` (true forces of the interior atoms vs the oracle), sizes and timings.
     ``sd`` / ``cfg``: oracle-format state dict and config of ``model`` (tests/util.make_model)."""
@@ -81,6 +81,11 @@ def cutout_parity(model, sd, cfg, pos, Z, cell, r_in: float = 4.0, centre: int |
            "E_region": float(eo[0].detach()),
            "max_dF": float((grad_A[ids].cpu() - go).abs().max()), "max_F": float(go.abs().max()),
            "seconds_product": t_gpu, "seconds_oracle": t_cpu}
+    if fp64_reference:       # context for the fp32 bar: both fp32 implementations against the same sum evaluated in float64
+        sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+        e64 = O.FORWARDS[kind](sd64, cfg, pc.double(), zc, ei, cell2.double(), es.double(), batch, 2)[0].detach()
+        out["rel_dE_vs_fp64"] = float((e_A.detach().cpu().double().sum() - e64).abs() / e64.abs().clamp(min=1e-30))
+        out["oracle_fp32_vs_fp64"] = float((eo[0].detach().double() - e64).abs() / e64.abs().clamp(min=1e-30))
     if check_full_forces:
         p2 = pos.detach().clone().requires_grad_(True)
         e_full, _, _ = model.forward_graph(p2, Z, cell.reshape(-1, 3, 3), g)
