@@ -46,6 +46,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--micro", type=int, default=4, help="C2: graphs per micro-batch")
+    ap.add_argument("--skin", type=float, default=0.4, help="C3: Verlet skin in Angstrom")
+    ap.add_argument("--graph-skin", type=float, default=1.0, help="C3: Verlet skin of the CUDA-graph variant")
     ap.add_argument("--cuda-graph", type=int, default=1, help="C4: replay the resident step as ONE captured CUDA graph (0: eager launches)")
     return ap.parse_args()
 
@@ -357,12 +359,87 @@ def run_c2(args):
 
 
 # --------------------------------------------------------------------------------------------------------------
+def run_c3(args):
+    """``--workload C3`` (BASELINE.json configs[2]): HTNet L=3 F=128 on the synthetic 31 944-atom water box, MD through the
+    ASE-style calculator plugin on one B200.  A step = one velocity-Verlet step (neighbour list or Verlet-skin re-use, energy +
+    forces, integration).  ``value``: the device-resident loop (``plugin.md.velocity_verlet_device``, positions / velocities /
+    forces never leave the GPU); ``e2e``: the host-driven loop through ``NNCalculator.calculate`` (numpy positions in, numpy
+    forces out every step -- what ASE's ``VelocityVerlet`` does, plugin/ase_interface/calculator.py:42-57)."""
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback")
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    import hermnet_b200 as H
+    from hermnet_b200 import ops, synthetic
+    from hermnet_b200.plugin import md
+    from hermnet_b200.plugin.calculator import NNCalculator
+    (pos, Z, cell), cfg = synthetic.config("C3", args.scale)
+    kind = cfg.pop("kind")
+    torch.manual_seed(1234)
+    model = getattr(H, kind)(**cfg).to(dev).eval()
+    for p_ in model.parameters():
+        p_.requires_grad_(False)
+    N = len(Z)
+    atoms = md.SimpleAtoms(Z, pos, cell)
+    md.maxwell_boltzmann(atoms, 300.0, seed=3)
+    v0 = atoms.velocities.copy()
+    skin = args.skin
+    out = {}
+    variants = [("rebuild", 0.0, False), ("skin", skin, False), ("skin_graph", max(skin, args.graph_skin), True)]
+    for name, sk, cg in variants:
+        st = {}
+        try:
+            md.velocity_verlet_device(model, Z, pos, cell, v0, steps=max(3, args.warmup), dt_fs=0.5, device=dev, skin=sk, cuda_graph=cg)
+            torch.cuda.synchronize()
+            ops.LAUNCHES["n"] = 0
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            _, _, e = md.velocity_verlet_device(model, Z, pos, cell, v0, steps=args.steps, dt_fs=0.5, device=dev, skin=sk, stats=st,
+                                                cuda_graph=cg)
+            b.record()
+            torch.cuda.synchronize()
+            out[name] = (a.elapsed_time(b) / (args.steps + 1), st, ops.LAUNCHES["n"], float(e[-1]), sk)     # (+1: the initial force call)
+        except Exception as exc:  # noqa: BLE001 -- a variant that cannot run is reported, not fatal
+            out[name] = (float("inf"), {"error": f"{type(exc).__name__}: {str(exc)[:160]}"}, 0, float("nan"), sk)
+    calc = NNCalculator(model, None, trn_mean=0.0, device_="cuda", ensemble="NVT", skin=skin)
+    atoms.calc = calc
+    md.velocity_verlet(atoms, steps=2, dt_fs=0.5)
+    torch.cuda.synchronize()
+    w0 = time.perf_counter()
+    md.velocity_verlet(atoms, steps=max(1, args.e2e_steps), dt_fs=0.5)
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - w0) / (max(1, args.e2e_steps) + 1)
+    best = min(out, key=lambda k: out[k][0])
+    ms = out[best][0]
+    how = {"rebuild": "rebuilt every step", "skin": f"Verlet skin {out['skin'][4]} A, list re-used while valid",
+           "skin_graph": f"Verlet skin {out['skin_graph'][4]} A, list re-used while valid and the whole evaluation replayed as one CUDA "
+                         f"graph per step (captured once per list build, capture time included)"}[best]
+    line = {"metric": "atom-steps/s (MD step: energy+forces)", "value": N / (ms * 1e-3), "unit": "atom-steps/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"C3: {kind} L={cfg['num_layers']} F={cfg['hidden_channels']} K={cfg['num_rbf']} rc={cfg['rc']} on the {N}-atom "
+                                   f"water box, velocity-Verlet MD (0.5 fs, 300 K) through the calculator plugin; neighbour list: " + how
+                                   + ("" if args.scale == 1.0 else f" [scale={args.scale}: NOT the BASELINE size]"),
+                       "parallelism": "single GPU", "l2_policy": "per-step tensors exceed L2; no flush needed"},
+            "variants": {k: {"ms_per_step": v[0], "skin_A": v[4], "list": v[1], "final_energy": v[3]} for k, v in out.items()},
+            "e2e": {"value": N / e2e_s, "unit": "atom-steps/s", "h2d_bytes_per_step": int(N * 3 * 4 + N * 8 + 36),
+                    "d2h_bytes_per_step": int(N * 3 * 4 + 4), "ms_per_step": 1e3 * e2e_s,
+                    "includes": "numpy positions -> H2D, (re-used) neighbour list, energy + forces, D2H of forces, host integration"},
+            "gpu_launches": out[best][2], "roofline": None}
+    _finish(1, real_stdout, line)
+
+
+# --------------------------------------------------------------------------------------------------------------
 def main():
     args = parse_args()
     if args.impl == "reference":
         return run_reference(args)
     if args.workload == "C2":
         return run_c2(args)
+    if args.workload == "C3":
+        return run_c3(args)
     if args.workload == "C5":      # 30 rows per atom: 20 GB tensors; avoid losing tens of GB to allocator fragmentation
         os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
 

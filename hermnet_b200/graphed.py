@@ -39,18 +39,16 @@ class GraphedForces:
         return self.energy, self.grad
 
 
-def graphed_forces(model, pos: Tensor, atomic_number: Tensor, cell: Optional[Tensor], graph) -> GraphedForces:
+def graphed_forces(model, pos: Tensor, atomic_number: Tensor, cell: Optional[Tensor], graph, warmup: int = 2) -> GraphedForces:
     """Captured ``energy, dE/dpos`` of ``model`` on the prebuilt ``graph`` (``model.build_graph``); parameters must be frozen
     (inference) and the graph must stay valid for the positions passed later (same edges, or a Verlet-skin superset list)."""
     if any(p.requires_grad for p in model.parameters()):
         raise RuntimeError("hermnet_b200.graphed_forces: freeze the parameters first (inference path)")
-    if getattr(graph, "masked", False):
-        raise RuntimeError("hermnet_b200.graphed_forces: Verlet-skin graphs compute a per-call live mask on the host side; "
-                           "capture a plain graph")
+    # (a Verlet-skin superset list works too: its per-call live mask is computed by device kernels inside the capture)
 
     def fn(p):
         q = p.detach().requires_grad_(True)
         e, _, _ = model.forward_graph(q, atomic_number, cell, graph)
         (g,) = torch.autograd.grad(e.sum(), q)
         return e.detach(), g
-    return GraphedForces(fn, pos)
+    return GraphedForces(fn, pos, warmup)

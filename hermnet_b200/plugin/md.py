@@ -84,10 +84,29 @@ class VerletGraph:
     (Sub-networks are treated as active when the SUPERSET list has an edge for them -- hermnet.py:56-57 can only differ
     for a sub-network whose every edge sits in the skin shell.)"""
 
-    def __init__(self, model, skin: float = 0.0):
+    def __init__(self, model, skin: float = 0.0, cuda_graph: bool = False):
         self.model, self.skin = model, float(skin)
         self.graph, self.ref_pos, self.ref_cell, self.ref_Z = None, None, None, None
         self.builds = self.reuses = 0
+        # cuda_graph: while a list is re-used, replay the whole evaluation (forward + backward, ~200 launches + torch glue) as
+        # ONE captured CUDA graph -- small systems are bound by host launch latency, not by the kernels
+        self.cuda_graph = bool(cuda_graph) and self.skin > 0.0
+        self._captured, self._captured_for = None, None
+
+    def energy_and_gradient(self, pos, Z, cell):
+        """``(E [num_graphs], dE/dpos)`` at ``pos`` through the re-used (or rebuilt) list; with ``cuda_graph`` the evaluation is
+        captured once per list build and replayed afterwards (the returned tensors are then the capture's static outputs)."""
+        g = self.get(pos, Z, cell)
+        if self.cuda_graph and pos.is_cuda:
+            if self._captured_for is not g:
+                from ..graphed import graphed_forces
+                self._captured = graphed_forces(self.model, pos, Z, cell, g, warmup=1)
+                self._captured_for = g
+            return self._captured(pos)
+        p = pos.detach().requires_grad_(True)
+        e, _, _ = self.model.forward_graph(p, Z, None if cell is None else cell.reshape(-1, 3, 3), g)
+        (grad,) = torch.autograd.grad(e.sum(), p)
+        return e.detach(), grad
 
     def get(self, pos, Z, cell):
         p = pos.detach()
@@ -106,7 +125,7 @@ class VerletGraph:
 
 
 def velocity_verlet_device(model, numbers, positions, cell, velocities, steps: int, dt_fs: float = 0.5, device="cuda",
-                           skin: float = 0.0, stats: dict = None):
+                           skin: float = 0.0, stats: dict = None, cuda_graph: bool = False):
     """Device-resident MD: positions, velocities and forces never leave the GPU; with ``skin > 0`` the
     neighbour list / row CSR / tile plans are re-used across steps (``VerletGraph``), otherwise rebuilt per step (device
     cell list).  ``stats`` (optional dict) receives the build / re-use counts."""
@@ -117,9 +136,12 @@ def velocity_verlet_device(model, numbers, positions, cell, velocities, steps: i
     c = torch.as_tensor(np.asarray(cell), dtype=torch.float32).reshape(1, 3, 3).to(dev)
     masses = np.array([MASSES.get(int(z), 2.0 * int(z)) for z in np.asarray(numbers)])
     inv_m = torch.as_tensor(1.0 / (masses * AMU_A2_FS2_TO_EV), dtype=torch.float32).to(dev)[:, None]
-    vg = VerletGraph(model, skin)
+    vg = VerletGraph(model, skin, cuda_graph)
 
     def forces(p):
+        if vg.cuda_graph:
+            e, g = vg.energy_and_gradient(p, Z, c)
+            return e.clone(), -g                 # (static outputs of the capture: copy what outlives the next call)
         d = Data(pos=p.detach().requires_grad_(True), atomic_number=Z, cell=c)
         d.graph = vg.get(d.pos, Z, c)
         e = model(d)

@@ -15,6 +15,15 @@ def load(path):
         u = x["Metric Unit"]
         v = v / 1e6 if u == "ns" else (v / 1e3 if u.startswith("us") else v)
         name = x["Kernel Name"]
+        t = re.search(r"edge_tc_kernel<(?:\(int\))?(\d), (?:\(bool\))?(\d|true|false)", name)
+        if t:
+            out.append((["edge_tc_fwd", "edge_tc_bwd_dst", "edge_tc_bwd_src"][int(t.group(1))], v))
+            continue
+        m = re.search(r"(gemm_tf32x3_kernel|node_\w+_kernel|halo_\w+_kernel|tile_windows_kernel|split_weights_kernel|plan_\w+_kernel|"
+                      r"basis_index_kernel|split_tf32\w*_kernel)", name)
+        if m:
+            out.append((m.group(1), v))
+            continue
         m = re.search(r"(edge_\w+_kernel|rg_\w+_kernel|segment_sum\w*_kernel|gather_rows\w*_kernel|expand_rowptr_kernel|"
                       r"key_hist_kernel|graph_\w+_kernel|bin_atoms_kernel|gather_sorted_kernel|triplet\w+_kernel)", name)
         short = m.group(1) if m else re.sub(r"<.*", "", name).replace("void ", "")[:60]

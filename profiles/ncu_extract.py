@@ -12,6 +12,7 @@ import collections
 import csv
 import json
 import os
+import re
 import subprocess
 import sys
 
@@ -24,7 +25,8 @@ WANT = [
     ("sm__inst_executed.avg.per_cycle_elapsed", "IPC"), ("sm__warps_active.avg.pct_of_peak_sustained_active", "occupancy %"),
     ("launch__registers_per_thread", "regs"), ("smsp__inst_executed.sum", "warp instr"),
 ]
-TIMER = {"edge_fwd": "painn_edge_fwd", "edge_bwd_dst": "painn_edge_bwd_dst", "edge_bwd_src": "painn_edge_bwd_src"}
+TIMER = {"edge_fwd": "painn_edge_fwd", "edge_bwd_dst": "painn_edge_bwd_dst", "edge_bwd_src": "painn_edge_bwd_src",
+         "edge_tc_fwd": "painn_edge_fwd", "edge_tc_bwd_dst": "painn_edge_bwd_dst", "edge_tc_bwd_src": "painn_edge_bwd_src"}
 
 
 def to_gb(v, unit):
@@ -43,6 +45,9 @@ def main():
     for r in rows[2:]:
         name = r[ix["Kernel Name"]]
         short = name.split("::")[-1].split("(")[0]
+        m = re.search(r"edge_tc_kernel<(?:\(int\))?(\d), (?:\(bool\))?(\d|true|false)", name)
+        if m:       # tensor-core edge kernels: template <MODE, HV, DBG>
+            short = ["edge_tc_fwd", "edge_tc_bwd_dst", "edge_tc_bwd_src"][int(m.group(1))] + ("" if m.group(2) in ("1", "true") else "[vec=NULL]")
         rec = {"kernel": short}
         for key, label in WANT:
             if key not in ix:
@@ -62,7 +67,7 @@ def main():
         table.append(rec)
         rawrows.append([short] + [r[ix[k]] for k, _ in WANT if k in ix])
         for frag, timer in TIMER.items():
-            if frag in short:
+            if frag in short and "[vec=NULL]" not in short:      # (the first-layer variants read an L1-resident table)
                 traffic[timer].append(1e9 * (rec.get("GB rd", 0.0) + rec.get("GB wr", 0.0)))
     cols = ["kernel"] + [l for _, l in WANT if l != "warp instr"] + (["instr/edge"] if n_edges else []) + ["top stalls"]
     with open(out + "_summary.md", "w") as f:

@@ -347,3 +347,23 @@ def test_verlet_skin_list_reuse_on_gpu(kind, pbc_shift):
         assert runs[0.8][2]["builds"] == 1 and runs[0.8][2]["reuses"] == 8
         assert float((runs[0.0][0] - runs[0.8][0]).abs().max()) < 1e-4
         assert util.rel_err(runs[0.8][1], runs[0.0][1]) < 1e-5
+
+
+def test_device_md_with_cuda_graph_replay_follows_the_eager_trajectory():
+    """The Verlet-skin MD loop with the evaluation captured as one CUDA graph per list build (plugin/md.py, graphed.py)
+    gives the trajectory of the eager loop."""
+    from hermnet_b200.plugin import md
+    pos, Z, cell = synthetic.water_box(5, seed=9)
+    torch.manual_seed(11)
+    model = H.HTNet(elems=["H", "O"], rc=4.5, num_layers=2, hidden_channels=128, num_rbf=64).to(DEV).eval()
+    for p in model.parameters():
+        p.requires_grad_(False)
+    v0 = 0.003 * torch.randn(pos.shape, generator=torch.Generator().manual_seed(2)).numpy()
+    runs = {}
+    for cg in (False, True):
+        st = {}
+        p1, _, e1 = md.velocity_verlet_device(model, Z, pos, cell, v0, steps=8, dt_fs=0.5, device=DEV, skin=0.8, stats=st, cuda_graph=cg)
+        runs[cg] = (p1, e1, st)
+    assert runs[True][2] == runs[False][2] and runs[True][2]["reuses"] == 8
+    assert float((runs[True][0] - runs[False][0]).abs().max()) < 1e-5
+    assert util.rel_err(runs[True][1], runs[False][1]) < 1e-6
