@@ -381,6 +381,11 @@ def run_c3(args):
     model = getattr(H, kind)(**cfg).to(dev).eval()
     for p_ in model.parameters():
         p_.requires_grad_(False)
+    # random-init weights give forces of hundreds of eV/A: the "MD" would explode within a few steps and every list would be
+    # invalid at once.  Scale the last readout layer so that the synthetic trajectory moves like a real one (~0.01 A per
+    # step); the work per step does not depend on it.
+    model.out_energy[2].weight.mul_(1.0e-3)
+    model.out_energy[2].bias.mul_(1.0e-3)
     N = len(Z)
     atoms = md.SimpleAtoms(Z, pos, cell)
     md.maxwell_boltzmann(atoms, 300.0, seed=3)
@@ -420,7 +425,8 @@ def run_c3(args):
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"C3: {kind} L={cfg['num_layers']} F={cfg['hidden_channels']} K={cfg['num_rbf']} rc={cfg['rc']} on the {N}-atom "
-                                   f"water box, velocity-Verlet MD (0.5 fs, 300 K) through the calculator plugin; neighbour list: " + how
+                                   f"water box, velocity-Verlet MD (0.5 fs, 300 K; random-init weights, last readout layer x 1e-3 so that the trajectory "
+                                   f"stays physical) through the calculator plugin; neighbour list: " + how
                                    + ("" if args.scale == 1.0 else f" [scale={args.scale}: NOT the BASELINE size]"),
                        "parallelism": "single GPU", "l2_policy": "per-step tensors exceed L2; no flush needed"},
             "variants": {k: {"ms_per_step": v[0], "skin_A": v[4], "list": v[1], "final_energy": v[3]} for k, v in out.items()},

@@ -542,24 +542,25 @@ def tc_basis_index(geom: Tensor, inv_rc: float, num_rbf: int) -> Tensor:
     return kc
 
 
-def tc_plan_count(order: Tensor, kc: Tensor, grp_ptr: Tensor, n_groups: int, num_rbf: int) -> Tensor:
+def tc_plan_count(order: Tensor, kc: Tensor, grp_ptr: Tensor, n_groups: int, num_rbf: int, window: int = 32) -> Tensor:
     lib = _lib.load()
     dev = _chk("tc_plan_count", order, kc, grp_ptr)
     _i32("tc_plan_count", order, kc, grp_ptr)
     counts = torch.zeros(n_groups, dtype=torch.int32, device=dev)
     with torch.cuda.device(dev), _timed("tc_plan", dev):
-        _lib.check(lib.hn_tc_plan_count(_ptr(order), _ptr(kc), _ptr(grp_ptr), n_groups, int(num_rbf), _ptr(counts), _stream(dev)),
+        _lib.check(lib.hn_tc_plan_count(_ptr(order), _ptr(kc), _ptr(grp_ptr), n_groups, int(num_rbf), int(window), _ptr(counts), _stream(dev)),
                    "hn_tc_plan_count")
     return counts
 
 
-def tc_plan_fill(order: Tensor, kc: Tensor, grp_ptr: Tensor, n_groups: int, num_rbf: int, grp_tile: Tensor, n_tiles: int) -> Tensor:
+def tc_plan_fill(order: Tensor, kc: Tensor, grp_ptr: Tensor, n_groups: int, num_rbf: int, grp_tile: Tensor, n_tiles: int,
+                 window: int = 32) -> Tensor:
     lib = _lib.load()
     dev = _chk("tc_plan_fill", order, kc, grp_ptr, grp_tile)
     _i32("tc_plan_fill", order, kc, grp_ptr, grp_tile)
     tile_start = torch.empty(max(n_tiles, 1), dtype=torch.int32, device=dev)
     with torch.cuda.device(dev), _timed("tc_plan", dev):
-        _lib.check(lib.hn_tc_plan_fill(_ptr(order), _ptr(kc), _ptr(grp_ptr), n_groups, int(num_rbf), _ptr(grp_tile), _ptr(tile_start),
+        _lib.check(lib.hn_tc_plan_fill(_ptr(order), _ptr(kc), _ptr(grp_ptr), n_groups, int(num_rbf), int(window), _ptr(grp_tile), _ptr(tile_start),
                                        _stream(dev)), "hn_tc_plan_fill")
     return tile_start
 

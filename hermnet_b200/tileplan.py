@@ -30,6 +30,7 @@ class TilePlan:
         self.tile_win = torch.zeros((max(n_tiles, 1), 2), dtype=torch.int32, device=erec.device)
         self.tile_geom = torch.zeros((erec.size(0), 4), dtype=torch.float32, device=erec.device)
         self.zero_row = torch.zeros(512, dtype=torch.float32, device=erec.device)     # staged for masked (d >= rc) edges
+        self.window = 32           # basis-index width the tiles were cut for
         self.win_key = None        # (data_ptr, version) of the geometry the windows were computed for
         self._c = None
 
@@ -45,6 +46,7 @@ class TilePlan:
         q = TilePlan(self.kind, self.blk_info, self.blk_tile, self.tile_info, erec, self.n_blocks, self.n_tiles,
                      self.has_inactive, blk_xoff)
         q.tile_win, q.tile_geom = self.tile_win, self.tile_geom          # shared: they only depend on the geometry
+        q.window = self.window
         q._shared_with = self
         return q
 
@@ -60,18 +62,36 @@ class TilePlan:
             owner._win_pin = (geom, live)
 
 
+def _window(n_live: int, n_groups: int, num_rbf: int) -> int:
+    """Basis-index width of a tile: 32 (one k-chunk) when a group has enough edges to fill 64-edge tiles inside 32-wide
+    windows (HVNet blocks: ~430 edges over ~13 windows), wider for sparse groups (HPNet / HTNet rows, source blocks) -- a
+    half-empty tile costs the epilogue, the producers and the barriers as much as a full one, a second k-chunk only costs MMAs."""
+    import os
+    forced = os.environ.get("HERMNET_B200_TC_WINDOW")
+    if forced:
+        return int(forced)
+    per_group = n_live / max(n_groups, 1)
+    k32 = (num_rbf + 31) // 32 * 32
+    w = 32
+    while w < k32 and per_group * w / max(num_rbf, 1) < 48:      # expected edges per window below ~3/4 of a tile
+        w *= 2
+    return min(w, k32)
+
+
 def _tiles(order, kc, grp_ptr, n_groups, num_rbf, rec, grp_mod):
     """Greedy tiles of every group; returns (grp_tile [n_groups+1], tile_info, erec, n_tiles)."""
     dev = order.device
-    counts = ops.tc_plan_count(order, kc, grp_ptr, n_groups, num_rbf)
+    n_live_host = int(grp_ptr[n_groups])
+    window = _window(n_live_host, n_groups, num_rbf)
+    counts = ops.tc_plan_count(order, kc, grp_ptr, n_groups, num_rbf, window)
     grp_tile = torch.zeros(n_groups + 1, dtype=torch.int32, device=dev)
     torch.cumsum(counts, 0, dtype=torch.int32, out=grp_tile[1:])
     n_tiles, n_live = torch.stack([grp_tile[-1], grp_ptr[n_groups]]).tolist()       # one host sync per plan
-    tile_start = ops.tc_plan_fill(order, kc, grp_ptr, n_groups, num_rbf, grp_tile, n_tiles)
+    tile_start = ops.tc_plan_fill(order, kc, grp_ptr, n_groups, num_rbf, grp_tile, n_tiles, window)
     tile_mod = torch.repeat_interleave(grp_mod.to(torch.int32), counts.long()).contiguous() if n_tiles else \
         torch.zeros(1, dtype=torch.int32, device=dev)
     erec, tile_info = ops.tc_plan_finalize(order, tile_start, n_tiles, n_live, rec, tile_mod)
-    return grp_tile, tile_info, erec, n_tiles
+    return grp_tile, tile_info, erec, n_tiles, window
 
 
 def _sorted_by_group(kc: Tensor, grp: Tensor, n_groups: int, num_rbf: int):
@@ -130,10 +150,12 @@ def build_dst_plan(g, geom: Tensor, inv_rc: float, num_rbf: int) -> TilePlan:
     order, grp_ptr = _sorted_by_group(kc, grp, n_blocks, num_rbf)
     eid = torch.arange(E, device=dev, dtype=torch.int32)
     rec = torch.stack([(g.row_xoff[row] + g.col.long()).to(torch.int32), g.col, atom_local[atom].to(torch.int32), eid], 1).contiguous()
-    blk_tile, tile_info, erec, n_tiles = _tiles(order, kc, grp_ptr, n_blocks, num_rbf, rec, blk_mod)
+    blk_tile, tile_info, erec, n_tiles, window = _tiles(order, kc, grp_ptr, n_blocks, num_rbf, rec, blk_mod)
     blk_xoff = g.row_xoff[row0.reshape(-1)].to(torch.int32).contiguous() if n_blocks else None
-    return TilePlan("dst", blk_info, blk_tile, tile_info, erec, n_blocks, n_tiles, bool((~live).any().item()) if E else False,
+    plan = TilePlan("dst", blk_info, blk_tile, tile_info, erec, n_blocks, n_tiles, bool((~live).any().item()) if E else False,
                     blk_xoff)
+    plan.window = window
+    return plan
 
 
 def dst_plan_for_table(plan: TilePlan, g, g0) -> TilePlan:
@@ -166,9 +188,11 @@ def build_src_plan(g, geom: Tensor, inv_rc: float, num_rbf: int) -> TilePlan:
     eid = torch.arange(E, device=dev, dtype=torch.int32)
     rec = torch.stack([g.edge_row, (g.row_xoff[row] + col).to(torch.int32), (col - sblk * R).to(torch.int32), eid], 1).contiguous()
     grp_mod = torch.arange(M, device=dev).repeat(n_blocks)
-    grp_tile, tile_info, erec, n_tiles = _tiles(order, kc, grp_ptr, n_groups, num_rbf, rec, grp_mod)
+    grp_tile, tile_info, erec, n_tiles, window = _tiles(order, kc, grp_ptr, n_groups, num_rbf, rec, grp_mod)
     blk_tile = grp_tile[::M].contiguous()
-    return TilePlan("src", blk_info, blk_tile, tile_info, erec, n_blocks, n_tiles, bool((~live).any().item()) if E else False)
+    plan = TilePlan("src", blk_info, blk_tile, tile_info, erec, n_blocks, n_tiles, bool((~live).any().item()) if E else False)
+    plan.window = window
+    return plan
 
 
 def plans_of(g, geom: Tensor, inv_rc: float, num_rbf: int, want_src: bool):

@@ -216,9 +216,10 @@ int hn_tc_split_weights(const float *Wt, int32_t n_modules, int32_t num_rbf, int
                         float *wscale /*[M]*/, void *stream);
 int hn_tc_basis_index(const float *geom, int64_t n_edges, float inv_rc, int32_t num_rbf, int32_t *kc /*[E]*/, void *stream);
 int hn_tc_plan_count(const int32_t *order, const int32_t *kc, const int32_t *grp_ptr, int32_t n_groups, int32_t num_rbf,
-                     int32_t *counts /*[n_groups]*/, void *stream);
+                     int32_t window /* 32, 64, ...: basis-index width of a tile (k-chunks per tile = window / 32) */,
+                     int32_t *counts, void *stream);
 int hn_tc_plan_fill(const int32_t *order, const int32_t *kc, const int32_t *grp_ptr, int32_t n_groups, int32_t num_rbf,
-                    const int32_t *grp_tile /*[n_groups+1]*/, int32_t *tile_start /*[n_tiles]*/, void *stream);
+                    int32_t window, const int32_t *grp_tile, int32_t *tile_start, void *stream);
 int hn_tc_plan_finalize(const int32_t *order, const int32_t *tile_start, int32_t n_tiles, int64_t n_edges,
                         const int32_t *rec /*[E][4]*/, const int32_t *tile_mod, int32_t *erec, int32_t *tile_info, void *stream);
 /* live: NULL, or uint8 [E] -- 0 marks an entry of a Verlet-skin superset list that is not an edge now (stored as -d in

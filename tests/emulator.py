@@ -260,20 +260,20 @@ def tc_basis_index(geom, inv_rc, num_rbf):
     return torch.where(u < 1, kc, torch.full_like(kc, num_rbf - 1)).to(torch.int32)
 
 
-def _tc_fits(kc, k0, K):
-    return kc >= K - 1 or min(kc + 6, K - 1) <= k0 + TC_KC - 1
+def _tc_fits(kc, k0, K, W=32):
+    return kc >= K - 1 or min(kc + 6, K - 1) <= k0 + W - 1
 
 
 def _tc_window_start(kc, K):
     return 0 if kc >= K - 1 else (max(kc - 5, 0) & ~7)
 
 
-def _tc_tiles_of_group(ks, K):
+def _tc_tiles_of_group(ks, K, W=32):
     starts, start, k0 = [], 0, 0
     for i, k in enumerate(ks):
         if i == start:
             k0 = _tc_window_start(k, K)
-        elif i - start >= TC_TN or not _tc_fits(k, k0, K):
+        elif i - start >= TC_TN or not _tc_fits(k, k0, K, W):
             starts.append(start)
             start = i
             k0 = _tc_window_start(k, K)
@@ -282,18 +282,18 @@ def _tc_tiles_of_group(ks, K):
     return starts
 
 
-def tc_plan_count(order, kc, grp_ptr, n_groups, num_rbf):
+def tc_plan_count(order, kc, grp_ptr, n_groups, num_rbf, window=32):
     kk = kc[order.long()].tolist()
     gp = grp_ptr.tolist()
-    return torch.tensor([len(_tc_tiles_of_group(kk[gp[g]:gp[g + 1]], num_rbf)) for g in range(n_groups)], dtype=torch.int32)
+    return torch.tensor([len(_tc_tiles_of_group(kk[gp[g]:gp[g + 1]], num_rbf, window)) for g in range(n_groups)], dtype=torch.int32)
 
 
-def tc_plan_fill(order, kc, grp_ptr, n_groups, num_rbf, grp_tile, n_tiles):
+def tc_plan_fill(order, kc, grp_ptr, n_groups, num_rbf, grp_tile, n_tiles, window=32):
     kk = kc[order.long()].tolist()
     gp = grp_ptr.tolist()
     out = []
     for g in range(n_groups):
-        out += [gp[g] + s for s in _tc_tiles_of_group(kk[gp[g]:gp[g + 1]], num_rbf)]
+        out += [gp[g] + s for s in _tc_tiles_of_group(kk[gp[g]:gp[g + 1]], num_rbf, window)]
     assert len(out) == n_tiles
     return torch.tensor(out + ([0] if not out else []), dtype=torch.int32)
 
