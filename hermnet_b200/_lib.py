@@ -25,7 +25,7 @@ P = c_void_p  # every device pointer crosses the ABI as a plain address
 class TcPlan(Structure):
     """``hn_tc_plan``: tile plan of the tensor-core edge kernels (device pointers)."""
     _fields_ = [("n_blocks", c_int32), ("n_tiles", c_int32), ("blk_info", c_void_p), ("blk_tile", c_void_p),
-                ("blk_xoff", c_void_p), ("tile_info", c_void_p), ("tile_win", c_void_p), ("erec", c_void_p), ("tile_geom", c_void_p), ("zero_row", c_void_p)]
+                ("blk_xoff", c_void_p), ("tile_info", c_void_p), ("tile_win", c_void_p), ("erec", c_void_p), ("tile_geom", c_void_p), ("zero_row", c_void_p), ("blk_order", c_void_p)]
 
 
 # name -> (restype, argtypes); must list EVERY symbol of include/hermnet_b200.h (checked by tests/test_abi.py)

@@ -31,6 +31,7 @@ class TilePlan:
         self.tile_geom = torch.zeros((erec.size(0), 4), dtype=torch.float32, device=erec.device)
         self.zero_row = torch.zeros(512, dtype=torch.float32, device=erec.device)     # staged for masked (d >= rc) edges
         self.window = 32           # basis-index width the tiles were cut for
+        self.blk_order = None      # int32 [n_blocks] processing order (None: as stored)
         self.win_key = None        # (data_ptr, version) of the geometry the windows were computed for
         self._c = None
 
@@ -38,7 +39,8 @@ class TilePlan:
         if self._c is None:
             self._c = TcPlan(self.n_blocks, self.n_tiles, self.blk_info.data_ptr(), self.blk_tile.data_ptr(),
                              self.blk_xoff.data_ptr(), self.tile_info.data_ptr(), self.tile_win.data_ptr(),
-                             self.erec.data_ptr(), self.tile_geom.data_ptr(), self.zero_row.data_ptr())
+                             self.erec.data_ptr(), self.tile_geom.data_ptr(), self.zero_row.data_ptr(),
+                             None if self.blk_order is None else self.blk_order.data_ptr())
         return self._c
 
     def with_erec(self, erec: Tensor, blk_xoff: Tensor) -> "TilePlan":
@@ -47,6 +49,7 @@ class TilePlan:
                      self.has_inactive, blk_xoff)
         q.tile_win, q.tile_geom = self.tile_win, self.tile_geom          # shared: they only depend on the geometry
         q.window = self.window
+        q.blk_order = self.blk_order
         q._shared_with = self
         return q
 
@@ -76,6 +79,11 @@ def _window(n_live: int, n_groups: int, num_rbf: int) -> int:
     while w < k32 and per_group * w / max(num_rbf, 1) < 48:      # expected edges per window below ~3/4 of a tile
         w *= 2
     return min(w, k32)
+
+
+def _interleave() -> bool:
+    import os
+    return os.environ.get("HERMNET_B200_TC_INTERLEAVE", "1") != "0"       # (A/B switch)
 
 
 def _tiles(order, kc, grp_ptr, n_groups, num_rbf, rec, grp_mod):
@@ -155,6 +163,13 @@ def build_dst_plan(g, geom: Tensor, inv_rc: float, num_rbf: int) -> TilePlan:
     plan = TilePlan("dst", blk_info, blk_tile, tile_info, erec, n_blocks, n_tiles, bool((~live).any().item()) if E else False,
                     blk_xoff)
     plan.window = window
+    # processing order: every (element, owned/ghost) segment is Morton-ordered, so the chunk at fraction x of one segment is
+    # spatially close to the chunks at fraction x of the others -- visit them together (stable: slots of a chunk stay adjacent)
+    if _interleave() and n_blocks > 1:
+        seg_len = (seg_hi - seg_lo).clamp(min=1).double()
+        frac = (idx_in_seg.double() * R + 0.5 * R) / seg_len[seg_of_chunk]
+        key = frac.view(-1, 1).expand(-1, rpa).reshape(-1)
+        plan.blk_order = torch.sort(key, stable=True).indices.to(torch.int32).to(dev).contiguous()
     return plan
 
 
@@ -192,6 +207,13 @@ def build_src_plan(g, geom: Tensor, inv_rc: float, num_rbf: int) -> TilePlan:
     blk_tile = grp_tile[::M].contiguous()
     plan = TilePlan("src", blk_info, blk_tile, tile_info, erec, n_blocks, n_tiles, bool((~live).any().item()) if E else False)
     plan.window = window
+    if _interleave() and n_blocks > 1 and len(g.type_ptr) > 2:       # same idea for the source blocks (consecutive internal atoms)
+        tp = torch.tensor(g.type_ptr, dtype=torch.double)
+        first = (torch.arange(n_blocks, dtype=torch.double) * R + 0.5 * R).clamp(max=max(n - 1, 0))
+        seg = torch.clamp(torch.searchsorted(tp, first, right=True) - 1, 0, len(g.type_ptr) - 2)
+        lo_, hi_ = tp[seg], tp[seg + 1]
+        key = (first - lo_) / (hi_ - lo_).clamp(min=1.0)
+        plan.blk_order = torch.sort(key, stable=True).indices.to(torch.int32).to(dev).contiguous()
     return plan
 
 

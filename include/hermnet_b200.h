@@ -205,6 +205,9 @@ typedef struct {
     const int32_t *erec;
     float *tile_geom;          /* [E][4]: geometry of every record, written by hn_tc_tile_windows */
     const float *zero_row;     /* >= 3F zeros (required when hn_edge_params.flags bit 0 is set, else may be NULL) */
+    const int32_t *blk_order;  /* [n_blocks] processing order of the blocks (a permutation; NULL = identity).  Results do not
+                                  depend on it; interleaving the element-type slices spatially keeps the rows that several
+                                  sub-networks gather (vec, g_dx / g_dvec) in L2 between their uses. */
 } hn_tc_plan;
 
 int32_t hn_tc_supported(int32_t hidden, int32_t num_rbf);
