@@ -41,20 +41,6 @@ __device__ __forceinline__ u64 pk(float lo, float hi) {
     return r;
 }
 __device__ __forceinline__ void upk(u64 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
-    u64 d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-__device__ __forceinline__ void fma2a(u64 &acc, u64 a, u64 b) {    // acc += a * b (in place: spares the allocator a move)
-    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
-}
-__device__ __forceinline__ u64 mul2(u64 a, u64 b) {
-    u64 d;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-
 // NP packed pairs (= 2*NP consecutive channels) from global memory through the read-only path
 template <int NP>
 struct Pairs {
