@@ -72,6 +72,8 @@ SIGNATURES = {
     "hn_node_mid_bwd": (c_int32, [c_int64, c_int32, P, P, P, P, c_int64, P, P]),
     "hn_node_pre_bwd": (c_int32, [c_int64, c_int32, P, P, P, P, P, P, P]),
     "hn_gather_rows": (c_int32, [P, P, c_int64, c_int32, P, P]),
+    "hn_readout_fwd": (c_int32, [P, P, P, P, P, c_int64, c_int32, P, P]),
+    "hn_readout_bwd": (c_int32, [P, P, P, P, P, P, c_int64, c_int32, P, P]),
     "hn_halo_pack": (c_int32, [P, P, P, P, P, P, c_int64, c_int32, P]),
     "hn_halo_unpack": (c_int32, [P, P, c_int64, c_int32, P, P, P]),
     "hn_segment_sum_workspace_bytes": (c_int64, [c_int32, c_int32]),

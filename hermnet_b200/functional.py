@@ -239,6 +239,30 @@ def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor], tensor_cores: bool
     return torch.nn.functional.linear(x, weight, bias)
 
 
+class _Readout(Function):
+    """Readout MLP of frozen parameters (hermnet.py:129) in plain fp32 through ``hn_readout_{fwd,bwd}``."""
+
+    @staticmethod
+    def forward(ctx, x, W1, b1, W2, b2):
+        x = x.contiguous()
+        b2 = b2.detach().reshape(-1).contiguous()            # stays on the device: no host read-back (CUDA-graph capturable)
+        ctx.save_for_backward(x, W1, b1, W2, b2)
+        return ops.readout_fwd(x, W1.detach().contiguous(), b1.detach().contiguous(), W2.detach().reshape(-1).contiguous(), b2)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_e):
+        x, W1, b1, W2, b2 = ctx.saved_tensors
+        g_x = ops.readout_bwd(x, W1.detach().contiguous(), b1.detach().contiguous(), W2.detach().reshape(-1).contiguous(), b2,
+                              g_e.reshape(-1).contiguous())
+        return g_x, None, None, None, None
+
+
+def readout(x: Tensor, lin0, lin2) -> Tensor:
+    """``e_atom [N,1]`` of the readout ``Sequential(Linear(F, F/2), ScaledSiLU, Linear(F/2, 1))`` with frozen parameters."""
+    return _Readout.apply(x, lin0.weight, lin0.bias, lin2.weight, lin2.bias)
+
+
 # ----------------------------------------------------------------------------------------------------
 # fused node side of one HVNet layer (frozen parameters): two autograd nodes per layer instead of ~60
 # ----------------------------------------------------------------------------------------------------

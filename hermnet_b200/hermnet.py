@@ -67,8 +67,8 @@ class _HermNet(nn.Module):
         self.edge_path = "auto"       # 'auto' | 'fused' | 'composite'
         self.tensor_core_linear = True   # fused path: node-side nn.Linear layers run on tcgen05 (3xTF32 split)
         self.fused_node = True           # frozen HVNet parameters: fused node-side kernels with hand-written backward
-        # readout MLP (hermnet.py:129) in plain fp32 instead of the 3xTF32 tensor-core GEMM: N x F x F/2 FLOP, negligible time,
-        # and the per-atom energies are a cancelling sum -- measured on the C4 cut-out check: |dE|/|E| 7.1e-6 -> 5.1e-6
+        # readout MLP (hermnet.py:129) in plain fp32 (hn_readout_{fwd,bwd}) instead of the 3xTF32 tensor-core GEMM: N x F x F/2
+        # FLOP, negligible time, and the per-atom energies are a cancelling sum -- C4 cut-out check: |dE|/|E| 7.1e-6 -> 5.1e-6
         self.readout_fp32 = True
         self.store_features = False   # write data.x / data.vec back like the reference does (hermnet.py:63-64)
         # None: recompute every layer in the backward pass instead of keeping its activations (torch.utils.checkpoint)
@@ -199,9 +199,13 @@ class _HermNet(nn.Module):
             else:
                 x, vec = self._layer(conv, x, vec, geom, g, p, vec_zero=(li == 0), z0=z_i if li == 0 else None,
                                      live=None if fused else live_c)
-        tc = fused and self.tensor_core_linear and not self.readout_fp32
-        h = self.out_energy[1](Fn.linear(x, self.out_energy[0].weight, self.out_energy[0].bias, tc))
-        e_atom = self.out_energy[2](h)                                   # [N,1]   hermnet.py:129
+        if (fused and self.readout_fp32 and F in (64, 128) and x.dtype == torch.float32
+                and not any(q.requires_grad for q in self.out_energy.parameters())):
+            e_atom = Fn.readout(x, self.out_energy[0], self.out_energy[2])     # [N,1]   hermnet.py:129, own fp32 kernel
+        else:
+            tc = fused and self.tensor_core_linear and not self.readout_fp32
+            h = self.out_energy[1](Fn.linear(x, self.out_energy[0].weight, self.out_energy[0].bias, tc))
+            e_atom = self.out_energy[2](h)                               # [N,1]   hermnet.py:129
         if atom_weight is not None:
             e_atom = e_atom * atom_weight.to(e_atom.dtype)[g.perm].unsqueeze(1)
         sb = g.seg_batch

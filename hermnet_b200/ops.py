@@ -340,6 +340,29 @@ def gather_rows(X: Tensor, idx: Tensor) -> Tensor:
     return out
 
 
+def readout_fwd(x: Tensor, W1: Tensor, b1: Tensor, W2: Tensor, b2: Tensor) -> Tensor:
+    """``e_atom [N,1] = W2 . ssilu(W1 x + b1) + b2`` in plain fp32 (hn_readout_fwd)."""
+    lib = _lib.load()
+    dev = _chk("readout_fwd", x, W1, b1, W2, b2)
+    _f32("readout_fwd", x, W1, b1, W2, b2)
+    out = torch.empty((x.size(0), 1), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev), _timed("readout", dev):
+        _lib.check(lib.hn_readout_fwd(_ptr(x), _ptr(W1), _ptr(b1), _ptr(W2), _ptr(b2), x.size(0), x.size(1), _ptr(out), _stream(dev)),
+                   "hn_readout_fwd")
+    return out
+
+
+def readout_bwd(x: Tensor, W1: Tensor, b1: Tensor, W2: Tensor, b2: Tensor, g_e: Tensor) -> Tensor:
+    lib = _lib.load()
+    dev = _chk("readout_bwd", x, W1, b1, W2, b2, g_e)
+    _f32("readout_bwd", x, W1, b1, W2, b2, g_e)
+    g_x = torch.empty_like(x)
+    with torch.cuda.device(dev), _timed("readout", dev):
+        _lib.check(lib.hn_readout_bwd(_ptr(x), _ptr(W1), _ptr(b1), _ptr(W2), _ptr(b2), _ptr(g_e), x.size(0), x.size(1), _ptr(g_x),
+                                      _stream(dev)), "hn_readout_bwd")
+    return g_x
+
+
 def halo_pack(x: Tensor, vec: Tensor, src_idx: Tensor, row_peer: Tensor, row_slot: Tensor, dst_base: Tensor) -> None:
     """Rows ``[x | vec]`` of the atoms ``src_idx`` stored at ``dst_base[row_peer[i]] + row_slot[i] * 4F`` floats (device
     addresses: peers' landing buffers over NVLink, or slices of a local send buffer)."""

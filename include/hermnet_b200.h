@@ -254,6 +254,17 @@ int hn_segment_sum(const float *Y, const int32_t *rowptr, const int32_t *perm, i
                    float *out, void *workspace, int64_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Readout MLP (hermnet.py:112-116,129): e_atom[i] = W2 . ssilu(W1 x[i] + b1) + b2, W1 [F/2, F], W2 [F/2], plain fp32 FMAs
+ * (the atomic energies cancel strongly in the sum; this layer does not use the 3xTF32 GEMM).  bwd: g_x[i] = dE/dx[i] given
+ * g_e[i] = dL/de_atom[i]; the hidden activations are recomputed.  F = 64 or 128 (W1 lives in shared memory); b2: device
+ * pointer to the scalar bias (no host read-back: the call can be captured in a CUDA graph).
+ * ------------------------------------------------------------------------------------------- */
+int hn_readout_fwd(const float *x, const float *W1, const float *b1, const float *W2, const float *b2, int64_t n, int32_t hidden,
+                   float *e_atom, void *stream);
+int hn_readout_bwd(const float *x, const float *W1, const float *b1, const float *W2, const float *b2, const float *g_e, int64_t n,
+                   int32_t hidden, float *g_x, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Halo exchange of the domain-decomposed path (no counterpart in the reference, whose only
  * multi-GPU path is DDP, example/dist_train.py).  A landing-buffer row is [x (F) | vec (3F)] floats.
  *   hn_halo_pack:   row i = features of atom src_idx[i]; stored at

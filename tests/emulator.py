@@ -432,6 +432,18 @@ def tc_edge_bwd_src(p, plan, xh, vec, geom, wsplit, wscale, bias, offset, g_dx, 
     return grad_xh, grad_vec
 
 
+def readout_fwd(x, W1, b1, W2, b2):
+    h = x @ W1.t() + b1
+    return (_ssilu(h) @ W2.reshape(-1, 1)) + b2
+
+
+def readout_bwd(x, W1, b1, W2, b2, g_e):
+    h = x @ W1.t() + b1
+    sg = torch.sigmoid(h)
+    dh = sg * (1 + h * (1 - sg)) / 0.6
+    return ((g_e.reshape(-1, 1) * W2.reshape(1, -1)) * dh) @ W1
+
+
 def gather_rows(X, idx):
     return X[idx.long()].contiguous()
 
@@ -534,7 +546,7 @@ def install(monkeypatch):
                  "painn_edge_bwd_src", "painn_edge_bwd_w", "gemm_tf32x3_ex", "node_pre", "node_mid", "node_post",
                  "node_post_bwd", "node_mid_bwd", "node_pre_bwd", "gather_rows", "segment_sum", "gemm_tf32x3", "split_tf32",
                  "tc_supported", "tc_block_rows", "tc_groups", "tc_split_weights", "tc_basis_index", "tc_plan_count", "tc_plan_fill",
-                 "tc_plan_finalize", "tc_tile_windows", "tc_edge_fwd", "tc_edge_bwd_dst", "tc_edge_bwd_src"):
+                 "tc_plan_finalize", "tc_tile_windows", "tc_edge_fwd", "tc_edge_bwd_dst", "tc_edge_bwd_src", "readout_fwd", "readout_bwd"):
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(ops, "require_cuda", lambda t, what: None)
     monkeypatch.setattr(ops, "compute_device", lambda t: t.device)

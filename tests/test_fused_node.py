@@ -72,3 +72,26 @@ def test_fused_node_path_on_the_golden_water_box():
     e, f, gc = util.energy_forces(model, data)
     assert util.rel_err(e.cpu(), case["energy"]) < 1e-5
     assert float((f.cpu() - case["forces"]).abs().max()) < 1e-4
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("F", [64, 128])
+def test_readout_kernels_match_float64(F):
+    """hn_readout_{fwd,bwd} (plain fp32 readout MLP, hermnet.py:129) against a float64 evaluation."""
+    from hermnet_b200 import ops
+    gen = torch.Generator().manual_seed(F)
+    n, Hd = 1000, F // 2
+    x = torch.randn(n, F, generator=gen).cuda()
+    W1 = (torch.randn(Hd, F, generator=gen) / F ** 0.5).cuda()
+    b1 = (0.1 * torch.randn(Hd, generator=gen)).cuda()
+    W2 = (torch.randn(Hd, generator=gen) / Hd ** 0.5).cuda()
+    b2t = torch.tensor([0.3]).cuda()
+    b2 = 0.3
+    ge = torch.randn(n, generator=gen).cuda()
+    e = ops.readout_fwd(x, W1, b1, W2, b2t)
+    gx = ops.readout_bwd(x, W1, b1, W2, b2t, ge)
+    xd = x.double().requires_grad_(True)
+    ed = (torch.nn.functional.silu(xd @ W1.double().t() + b1.double()) / 0.6) @ W2.double() + b2
+    (gd,) = torch.autograd.grad((ed * ge.double()).sum(), xd)
+    assert float((e.squeeze(1).double() - ed).abs().max()) < 2e-6 * max(1.0, float(ed.abs().max()))
+    assert float((gx.double() - gd).abs().max()) < 2e-6 * max(1.0, float(gd.abs().max()))

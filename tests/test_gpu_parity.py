@@ -367,3 +367,27 @@ def test_device_md_with_cuda_graph_replay_follows_the_eager_trajectory():
     assert runs[True][2] == runs[False][2] and runs[True][2]["reuses"] == 8
     assert float((runs[True][0] - runs[False][0]).abs().max()) < 1e-5
     assert util.rel_err(runs[True][1], runs[False][1]) < 1e-6
+
+
+def test_halo_pack_unpack_kernels():
+    """hn_halo_pack / hn_halo_unpack (csrc/hn_halo.cu) against torch indexing: rows [x | vec] scattered into two "peer" landing
+    buffers by (peer, slot), then moved into ghost rows in place."""
+    gen = torch.Generator().manual_seed(0)
+    n, F, n_send = 500, 128, 180
+    x = torch.randn(n, F, generator=gen).to(DEV)
+    vec = torch.randn(n, 3, F, generator=gen).to(DEV)
+    src = torch.randperm(n, generator=gen)[:n_send].to(torch.int32).to(DEV)
+    peer = (torch.arange(n_send) % 2).to(torch.int32).to(DEV)
+    slot = torch.cat([torch.randperm(90, generator=gen), torch.randperm(90, generator=gen)]).view(2, 90).t().reshape(-1)[:n_send].to(torch.int32).to(DEV)
+    bufs = [torch.zeros(90, 4 * F, device=DEV) for _ in range(2)]
+    base = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device=DEV)
+    ops.halo_pack(x, vec.view(n, 3 * F), src, peer, slot, base)
+    want = torch.cat([x, vec.view(n, 3 * F)], 1)
+    for p in range(2):
+        sel = peer == p
+        assert torch.equal(bufs[p][slot[sel].long()], want[src[sel].long()])
+    ghost = torch.arange(300, 390, dtype=torch.int32, device=DEV)
+    x2, v2 = x.clone(), vec.clone()
+    ops.halo_unpack(bufs[0], ghost, x2, v2.view(n, 3 * F))
+    assert torch.equal(x2[300:390], bufs[0][:, :F]) and torch.equal(v2[300:390].reshape(90, 3 * F), bufs[0][:, F:])
+    assert torch.equal(x2[:300], x[:300]) and torch.equal(v2[390:], vec[390:])

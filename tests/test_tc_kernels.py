@@ -27,6 +27,8 @@ def check_plan(plan, g, geom, K, inv_rc):
     n = int(info[:, 1].sum()) if nt else 0
     assert n == int(live.sum())
     assert int(bt[-1]) == nt and bool((bt[1:] >= bt[:-1]).all())
+    if plan.blk_order is not None:       # the processing order is a permutation of the blocks
+        assert torch.equal(torch.sort(plan.blk_order.cpu().long()).values, torch.arange(plan.n_blocks))
     if nt == 0:
         return
     assert int(info[:, 1].max()) <= 64 and int(info[:, 1].min()) >= 1
