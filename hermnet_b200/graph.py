@@ -323,7 +323,10 @@ class GraphBuilder:
         """``rowptr/col/shift`` is the base CSR with ``n_groups`` rows per atom (source-element groups)."""
         dev = col.device
         dbin = None
-        if pos_i is not None and col.numel() > 0:
+        # rows sorted by distance: only the FMA-pipe edge kernels (F != 128) sweep consecutive row entries with overlapping
+        # Gaussian bands; the tensor-core kernels regroup the edges in their tile plans, so the three sort passes are skipped
+        want_dbin = not (self.hidden is not None and self.num_rbf is not None and ops.edge_use_tc(self.hidden, self.num_rbf))
+        if want_dbin and pos_i is not None and col.numel() > 0:
             # sort every base row by distance (stable two-pass: distance bin, then row)
             dbin, base_row = self._distance_bins(pos_i, cell, atom_graph, rowptr, col, shift, self.n_groups)
             o1 = ops.sort_by_key(dbin, 256)[1].long()

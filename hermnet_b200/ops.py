@@ -565,6 +565,26 @@ def tc_basis_index(geom: Tensor, inv_rc: float, num_rbf: int) -> Tensor:
     return kc
 
 
+def tc_plan_sort(in_ptr: Tensor, ids: Optional[Tensor], kc: Tensor, sub: Optional[Tensor], n_seg: int, n_sub: int, num_rbf: int):
+    """Segment-local sort of the plan builder (``hn_tc_plan_sort``): returns ``(order int32 [n_live], grp_ptr int32
+    [n_seg * n_sub + 1])`` -- edge ids ordered by (segment, sub, kc) without the dropped (sub < 0) entries, and the start of
+    every (segment, sub) group in it.  One host-free count pass, a cumsum, one fill pass."""
+    lib = _lib.load()
+    dev = _chk("tc_plan_sort", in_ptr, ids, kc, sub)
+    _i32("tc_plan_sort", in_ptr, ids, kc, sub)
+    counts = torch.zeros(max(n_seg * n_sub, 1), dtype=torch.int32, device=dev)
+    grp_ptr = torch.zeros(n_seg * n_sub + 1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev), _timed("tc_plan", dev):
+        _lib.check(lib.hn_tc_plan_sort(_ptr(in_ptr), _ptr(ids), _ptr(kc), _ptr(sub), n_seg, n_sub, int(num_rbf), _ptr(counts), None, None,
+                                       _stream(dev)), "hn_tc_plan_sort")
+        torch.cumsum(counts[: n_seg * n_sub], 0, dtype=torch.int32, out=grp_ptr[1:])
+        out_base = grp_ptr[:: n_sub][:n_seg].contiguous()
+        order = torch.empty(max(int(kc.numel()), 1), dtype=torch.int32, device=dev)
+        _lib.check(lib.hn_tc_plan_sort(_ptr(in_ptr), _ptr(ids), _ptr(kc), _ptr(sub), n_seg, n_sub, int(num_rbf), None, _ptr(out_base),
+                                       _ptr(order), _stream(dev)), "hn_tc_plan_sort")
+    return order, grp_ptr
+
+
 def tc_plan_count(order: Tensor, kc: Tensor, grp_ptr: Tensor, n_groups: int, num_rbf: int, window: int = 32) -> Tensor:
     lib = _lib.load()
     dev = _chk("tc_plan_count", order, kc, grp_ptr)

@@ -62,7 +62,10 @@ class TilePlan:
         if owner.win_key != key:
             ops.tc_tile_windows(owner, geom, inv_rc, num_rbf, live)
             owner.win_key = key
-            owner._win_pin = (geom, live)
+            # keep the STORAGE alive (no address recycling while the cache entry lives) through a detached alias: the tensor
+            # itself carries its autograd node, whose context references the graph that owns this plan -- a cycle through
+            # C++ objects that no garbage collector would ever break
+            owner._win_pin = (geom.detach(), live)
 
 
 def _window(n_live: int, n_groups: int, num_rbf: int) -> int:
@@ -155,7 +158,15 @@ def build_dst_plan(g, geom: Tensor, inv_rc: float, num_rbf: int) -> TilePlan:
     live = g.row_mod.long()[row] >= 0
     grp = torch.where(live, blk, torch.full_like(blk, n_blocks)).to(torch.int32)
     kc = ops.tc_basis_index(geom, inv_rc, num_rbf)
-    order, grp_ptr = _sorted_by_group(kc, grp, n_blocks, num_rbf)
+    if rpa == 1 and n_blocks > 0 and num_rbf <= 8192:
+        # one row per atom: a block's edges are a contiguous range of the CSR -> sort every block in place (one warp per
+        # block, shared memory) instead of two global counting-sort passes over all E edges
+        bounds_rows = torch.cat([chunk_atom0, torch.tensor([n], device=dev)]).long()
+        in_ptr = g.rowptr[bounds_rows].contiguous()
+        sub = torch.where(live, torch.zeros_like(grp), torch.full_like(grp, -1)).contiguous()
+        order, grp_ptr = ops.tc_plan_sort(in_ptr, None, kc, sub, n_blocks, 1, num_rbf)
+    else:
+        order, grp_ptr = _sorted_by_group(kc, grp, n_blocks, num_rbf)
     eid = torch.arange(E, device=dev, dtype=torch.int32)
     rec = torch.stack([(g.row_xoff[row] + g.col.long()).to(torch.int32), g.col, atom_local[atom].to(torch.int32), eid], 1).contiguous()
     blk_tile, tile_info, erec, n_tiles, window = _tiles(order, kc, grp_ptr, n_blocks, num_rbf, rec, blk_mod)
@@ -199,7 +210,13 @@ def build_src_plan(g, geom: Tensor, inv_rc: float, num_rbf: int) -> TilePlan:
     n_groups = n_blocks * M
     grp = torch.where(live, sblk * M + mod, torch.full_like(sblk, n_groups)).to(torch.int32)
     kc = ops.tc_basis_index(geom, inv_rc, num_rbf)
-    order, grp_ptr = _sorted_by_group(kc, grp, n_groups, num_rbf)
+    if n_blocks > 0 and M * num_rbf <= 8192:
+        # a source block's edges are a contiguous range of the transposed CSR: segment-local sort by (sub-network, basis index)
+        sb = torch.arange(n_blocks + 1, device=dev, dtype=torch.long) * R
+        in_ptr = g.t_rowptr[sb.clamp(max=n)].contiguous()
+        order, grp_ptr = ops.tc_plan_sort(in_ptr, g.t_eid, kc, g.row_mod[row].contiguous(), n_blocks, M, num_rbf)
+    else:
+        order, grp_ptr = _sorted_by_group(kc, grp, n_groups, num_rbf)
     eid = torch.arange(E, device=dev, dtype=torch.int32)
     rec = torch.stack([g.edge_row, (g.row_xoff[row] + col).to(torch.int32), (col - sblk * R).to(torch.int32), eid], 1).contiguous()
     grp_mod = torch.arange(M, device=dev).repeat(n_blocks)

@@ -218,6 +218,12 @@ int64_t hn_tc_split_weights_elems(int32_t n_modules, int32_t hidden, int32_t num
 int hn_tc_split_weights(const float *Wt, int32_t n_modules, int32_t num_rbf, int32_t hidden, void *wsplit /*fp16*/,
                         float *wscale /*[M]*/, void *stream);
 int hn_tc_basis_index(const float *geom, int64_t n_edges, float inv_rc, int32_t num_rbf, int32_t *kc /*[E]*/, void *stream);
+/* Segment-local sort of the plan builder: segment s = entries in_ptr[s] .. in_ptr[s+1] of the edge list `ids` (NULL: identity)
+ * -- the CSR entries of a destination block or the transposed-CSR entries of a source block; entries are ordered by (sub, kc)
+ * inside their segment (sub: NULL = 0; -1 drops the entry), stable and deterministic.  Count pass: counts[s * n_sub + sub]
+ * (order_out NULL); fill pass: order_out[out_base[s] + position] = edge id (counts NULL).  n_sub * num_rbf <= 8192. */
+int hn_tc_plan_sort(const int32_t *in_ptr, const int32_t *ids, const int32_t *kc, const int32_t *sub, int32_t n_seg, int32_t n_sub,
+                    int32_t num_rbf, int32_t *counts, const int32_t *out_base, int32_t *order_out, void *stream);
 int hn_tc_plan_count(const int32_t *order, const int32_t *kc, const int32_t *grp_ptr, int32_t n_groups, int32_t num_rbf,
                      int32_t window /* 32, 64, ...: basis-index width of a tile (k-chunks per tile = window / 32) */,
                      int32_t *counts, void *stream);

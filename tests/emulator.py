@@ -282,6 +282,24 @@ def _tc_tiles_of_group(ks, K, W=32):
     return starts
 
 
+def tc_plan_sort(in_ptr, ids, kc, sub, n_seg, n_sub, num_rbf):
+    ip = in_ptr.tolist()
+    order, counts = [], torch.zeros(n_seg * n_sub, dtype=torch.int32)
+    for sg in range(n_seg):
+        items = torch.arange(ip[sg], ip[sg + 1])
+        e = items if ids is None else ids[items].long()
+        sb = torch.zeros_like(e) if sub is None else sub[e].long()
+        keep = sb >= 0
+        e, sb = e[keep], sb[keep]
+        o = torch.sort(sb * num_rbf + kc[e].long(), stable=True).indices
+        order.append(e[o])
+        counts[sg * n_sub:(sg + 1) * n_sub] = torch.bincount(sb, minlength=n_sub).to(torch.int32)
+    grp_ptr = torch.zeros(n_seg * n_sub + 1, dtype=torch.int32)
+    grp_ptr[1:] = torch.cumsum(counts, 0).to(torch.int32)
+    order = torch.cat(order).to(torch.int32) if order else torch.zeros(0, dtype=torch.int32)
+    return order, grp_ptr
+
+
 def tc_plan_count(order, kc, grp_ptr, n_groups, num_rbf, window=32):
     kk = kc[order.long()].tolist()
     gp = grp_ptr.tolist()
@@ -546,7 +564,7 @@ def install(monkeypatch):
                  "painn_edge_bwd_src", "painn_edge_bwd_w", "gemm_tf32x3_ex", "node_pre", "node_mid", "node_post",
                  "node_post_bwd", "node_mid_bwd", "node_pre_bwd", "gather_rows", "segment_sum", "gemm_tf32x3", "split_tf32",
                  "tc_supported", "tc_block_rows", "tc_groups", "tc_split_weights", "tc_basis_index", "tc_plan_count", "tc_plan_fill",
-                 "tc_plan_finalize", "tc_tile_windows", "tc_edge_fwd", "tc_edge_bwd_dst", "tc_edge_bwd_src", "readout_fwd", "readout_bwd"):
+                 "tc_plan_sort", "tc_plan_finalize", "tc_tile_windows", "tc_edge_fwd", "tc_edge_bwd_dst", "tc_edge_bwd_src", "readout_fwd", "readout_bwd"):
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(ops, "require_cuda", lambda t, what: None)
     monkeypatch.setattr(ops, "compute_device", lambda t: t.device)

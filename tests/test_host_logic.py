@@ -279,3 +279,30 @@ def test_device_md_reuses_the_verlet_list(emu):
     assert runs[0.5][2]["builds"] == 1 and runs[0.5][2]["reuses"] == 6
     assert float((runs[0.0][0] - runs[0.5][0]).abs().max()) < 1e-5
     assert util.rel_err(runs[0.5][1], runs[0.0][1]) < 1e-5
+
+
+@pytest.mark.parametrize("kind,elems", [("HVNet", ["Li", "Al", "Si", "O"]), ("HTNet", ["Li", "O"])])
+def test_graph_and_plans_are_released_without_the_garbage_collector(emu, kind, elems):
+    """A graph built by forward() (row CSR, tile plans, cached geometry) must die with its Data object by reference counting
+    alone: a cycle through an autograd node (plan -> geometry tensor -> grad_fn -> graph -> plan) would leak gigabytes per MD
+    step -- the cycle collector cannot see through C++ autograd nodes."""
+    import gc
+    import weakref
+    from tests.util import lattice_system
+    pos, Z, cell = lattice_system(4, [3, 13, 14, 8], 5)
+    torch.manual_seed(0)
+    model = getattr(H, kind)(elems=elems, rc=5.0, num_layers=2, hidden_channels=128, num_rbf=32).eval()
+    for p in model.parameters():
+        p.requires_grad_(False)
+    gc.collect()
+    gc.disable()
+    try:
+        d = H.Data(pos=pos.clone().requires_grad_(True), atomic_number=Z, cell=cell)
+        e = model(d)
+        (g,) = torch.autograd.grad(e.sum(), d.pos)
+        wg = weakref.ref(d.graph)
+        wp = weakref.ref(d.graph._lazy["tc_dst"])
+        del d, e, g
+        assert wg() is None and wp() is None
+    finally:
+        gc.enable()
