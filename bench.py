@@ -281,7 +281,7 @@ def run_c2(args):
     def step_e2e():
         graphs = [d.to(dev, non_blocking=True) for d in host]
         loss = parallel.force_matching_step_microbatched(ddp, graphs, opt, micro)
-        loss_h.copy_(loss.reshape(1), non_blocking=True)
+        loss_h.copy_(loss.detach().reshape(1), non_blocking=True)
         torch.cuda.synchronize()
 
     def barrier():
@@ -518,7 +518,7 @@ def main():
             e, g = engine.energy_forces(p)
         if rank == 0:
             f_h.copy_(-g, non_blocking=True)
-            e_h.copy_(e.reshape(1), non_blocking=True)
+            e_h.copy_(e.detach().reshape(1), non_blocking=True)   # (detach: copy_ from a grad-requiring source would chain every step's autograd graph -- and its row CSR -- onto e_h)
         torch.cuda.synchronize()
 
     def barrier():

@@ -23,6 +23,9 @@ for it in range(8):
     torch.cuda.synchronize(); t1 = time.perf_counter()
     (g,) = torch.autograd.grad(e.sum(), d.pos)
     torch.cuda.synchronize(); t2 = time.perf_counter()
-    f_h.copy_(-g, non_blocking=True); e_h.copy_(e.reshape(1), non_blocking=True)
+    f_h.copy_(-g, non_blocking=True); e_h.copy_(e.detach().reshape(1), non_blocking=True)
     torch.cuda.synchronize(); t3 = time.perf_counter()
-    print(f"it{it}: fwd {1e3*(t1-t0):.1f} bwd {1e3*(t2-t1):.1f} d2h {1e3*(t3-t2):.1f} total {1e3*(t3-t0):.1f} reserved {torch.cuda.memory_reserved()/2**30:.1f} GiB", flush=True)
+    print(f"it{it}: fwd {1e3*(t1-t0):.1f} bwd {1e3*(t2-t1):.1f} d2h {1e3*(t3-t2):.1f} total {1e3*(t3-t0):.1f} alloc {torch.cuda.memory_allocated()/2**30:.1f} max {torch.cuda.max_memory_allocated()/2**30:.1f} reserved {torch.cuda.memory_reserved()/2**30:.1f} GiB", flush=True)
+    torch.cuda.reset_peak_memory_stats()
+    if "--del" in sys.argv:
+        del d, e, g, p, z, c
