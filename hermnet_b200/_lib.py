@@ -56,6 +56,7 @@ SIGNATURES = {
     "hn_tc_split_weights_elems": (c_int64, [c_int32, c_int32, c_int32]),
     "hn_tc_split_weights": (c_int32, [P, c_int32, c_int32, c_int32, P, P, P]),
     "hn_tc_basis_index": (c_int32, [P, c_int64, c_float, c_int32, P, P]),
+    "hn_tc_plan_records": (c_int32, [c_int32, P, P, P, P, P, c_int32, c_int32, P, c_float, c_int32, c_int64, P, P, P, P]),
     "hn_tc_plan_sort": (c_int32, [P, P, P, P, c_int32, c_int32, c_int32, P, P, P, P]),
     "hn_tc_plan_count": (c_int32, [P, P, P, c_int32, c_int32, c_int32, P, P]),
     "hn_tc_plan_fill": (c_int32, [P, P, P, c_int32, c_int32, c_int32, P, P, P]),

@@ -565,6 +565,22 @@ def tc_basis_index(geom: Tensor, inv_rc: float, num_rbf: int) -> Tensor:
     return kc
 
 
+def tc_plan_records(g, geom: Tensor, inv_rc: float, num_rbf: int, src_major: bool, atom_local: Optional[Tensor], src_block: int):
+    """``(rec int32 [E,4], kc int32 [E], sub int32 [E])`` of a plan in one pass over the row-edges (``hn_tc_plan_records``)."""
+    lib = _lib.load()
+    dev = _chk("tc_plan_records", g.edge_row, g.col, g.row_xoff, g.row_mod, atom_local, geom)
+    _i32("tc_plan_records", g.edge_row, g.col, g.row_mod, atom_local)
+    E = int(g.n_edges)
+    rec = torch.empty((max(E, 1), 4), dtype=torch.int32, device=dev)
+    kc = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+    sub = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev), _timed("tc_plan", dev):
+        _lib.check(lib.hn_tc_plan_records(int(bool(src_major)), _ptr(g.edge_row), _ptr(g.col), _ptr(g.row_xoff), _ptr(g.row_mod),
+                                          _ptr(atom_local), int(g.rows_per_atom), int(src_block), _ptr(geom), float(inv_rc),
+                                          int(num_rbf), E, _ptr(rec), _ptr(kc), _ptr(sub), _stream(dev)), "hn_tc_plan_records")
+    return rec[:E], kc[:E], sub[:E]
+
+
 def tc_plan_sort(in_ptr: Tensor, ids: Optional[Tensor], kc: Tensor, sub: Optional[Tensor], n_seg: int, n_sub: int, num_rbf: int):
     """Segment-local sort of the plan builder (``hn_tc_plan_sort``): returns ``(order int32 [n_live], grp_ptr int32
     [n_seg * n_sub + 1])`` -- edge ids ordered by (segment, sub, kc) without the dropped (sub < 0) entries, and the start of

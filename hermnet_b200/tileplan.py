@@ -90,7 +90,7 @@ def _interleave() -> bool:
 
 
 def _tiles(order, kc, grp_ptr, n_groups, num_rbf, rec, grp_mod):
-    """Greedy tiles of every group; returns (grp_tile [n_groups+1], tile_info, erec, n_tiles)."""
+    """Greedy tiles of every group; returns (grp_tile [n_groups+1], tile_info, erec, n_tiles, window, n_live)."""
     dev = order.device
     n_live_host = int(grp_ptr[n_groups])
     window = _window(n_live_host, n_groups, num_rbf)
@@ -102,7 +102,7 @@ def _tiles(order, kc, grp_ptr, n_groups, num_rbf, rec, grp_mod):
     tile_mod = torch.repeat_interleave(grp_mod.to(torch.int32), counts.long()).contiguous() if n_tiles else \
         torch.zeros(1, dtype=torch.int32, device=dev)
     erec, tile_info = ops.tc_plan_finalize(order, tile_start, n_tiles, n_live, rec, tile_mod)
-    return grp_tile, tile_info, erec, n_tiles, window
+    return grp_tile, tile_info, erec, n_tiles, window, n_live
 
 
 def _sorted_by_group(kc: Tensor, grp: Tensor, n_groups: int, num_rbf: int):
@@ -152,27 +152,22 @@ def build_dst_plan(g, geom: Tensor, inv_rc: float, num_rbf: int) -> TilePlan:
     # per atom: chunk and position inside it
     atom_chunk = torch.repeat_interleave(torch.arange(n_chunks, device=dev), chunk_size.long())
     atom_local = torch.arange(n, device=dev) - chunk_atom0[atom_chunk]
-    row = g.edge_row.long()
-    atom = torch.div(row, rpa, rounding_mode="floor")
-    blk = atom_chunk[atom] * rpa + (row - atom * rpa)
-    live = g.row_mod.long()[row] >= 0
-    grp = torch.where(live, blk, torch.full_like(blk, n_blocks)).to(torch.int32)
-    kc = ops.tc_basis_index(geom, inv_rc, num_rbf)
+    rec, kc, sub = ops.tc_plan_records(g, geom, inv_rc, num_rbf, False, atom_local.to(torch.int32).contiguous(), 1)
     if rpa == 1 and n_blocks > 0 and num_rbf <= 8192:
         # one row per atom: a block's edges are a contiguous range of the CSR -> sort every block in place (one warp per
         # block, shared memory) instead of two global counting-sort passes over all E edges
         bounds_rows = torch.cat([chunk_atom0, torch.tensor([n], device=dev)]).long()
         in_ptr = g.rowptr[bounds_rows].contiguous()
-        sub = torch.where(live, torch.zeros_like(grp), torch.full_like(grp, -1)).contiguous()
         order, grp_ptr = ops.tc_plan_sort(in_ptr, None, kc, sub, n_blocks, 1, num_rbf)
     else:
+        row = g.edge_row.long()
+        atom = torch.div(row, rpa, rounding_mode="floor")
+        blk = atom_chunk[atom] * rpa + (row - atom * rpa)
+        grp = torch.where(sub >= 0, blk, torch.full_like(blk, n_blocks)).to(torch.int32)
         order, grp_ptr = _sorted_by_group(kc, grp, n_blocks, num_rbf)
-    eid = torch.arange(E, device=dev, dtype=torch.int32)
-    rec = torch.stack([(g.row_xoff[row] + g.col.long()).to(torch.int32), g.col, atom_local[atom].to(torch.int32), eid], 1).contiguous()
-    blk_tile, tile_info, erec, n_tiles, window = _tiles(order, kc, grp_ptr, n_blocks, num_rbf, rec, blk_mod)
+    blk_tile, tile_info, erec, n_tiles, window, n_live = _tiles(order, kc, grp_ptr, n_blocks, num_rbf, rec, blk_mod)
     blk_xoff = g.row_xoff[row0.reshape(-1)].to(torch.int32).contiguous() if n_blocks else None
-    plan = TilePlan("dst", blk_info, blk_tile, tile_info, erec, n_blocks, n_tiles, bool((~live).any().item()) if E else False,
-                    blk_xoff)
+    plan = TilePlan("dst", blk_info, blk_tile, tile_info, erec, n_blocks, n_tiles, n_live < E, blk_xoff)
     plan.window = window
     # processing order: every (element, owned/ghost) segment is Morton-ordered, so the chunk at fraction x of one segment is
     # spatially close to the chunks at fraction x of the others -- visit them together (stable: slots of a chunk stay adjacent)
@@ -202,27 +197,21 @@ def build_src_plan(g, geom: Tensor, inv_rc: float, num_rbf: int) -> TilePlan:
     n_blocks = (n + R - 1) // R
     b = torch.arange(n_blocks, device=dev, dtype=torch.long)
     blk_info = torch.stack([b * R, torch.ones_like(b), torch.clamp(n - b * R, max=R), torch.full_like(b, -1)], 1).to(torch.int32).contiguous()
-    row = g.edge_row.long()
-    mod = g.row_mod.long()[row]
-    col = g.col.long()
-    sblk = torch.div(col, R, rounding_mode="floor")
-    live = mod >= 0
     n_groups = n_blocks * M
-    grp = torch.where(live, sblk * M + mod, torch.full_like(sblk, n_groups)).to(torch.int32)
-    kc = ops.tc_basis_index(geom, inv_rc, num_rbf)
+    rec, kc, sub = ops.tc_plan_records(g, geom, inv_rc, num_rbf, True, None, R)
     if n_blocks > 0 and M * num_rbf <= 8192:
         # a source block's edges are a contiguous range of the transposed CSR: segment-local sort by (sub-network, basis index)
         sb = torch.arange(n_blocks + 1, device=dev, dtype=torch.long) * R
         in_ptr = g.t_rowptr[sb.clamp(max=n)].contiguous()
-        order, grp_ptr = ops.tc_plan_sort(in_ptr, g.t_eid, kc, g.row_mod[row].contiguous(), n_blocks, M, num_rbf)
+        order, grp_ptr = ops.tc_plan_sort(in_ptr, g.t_eid, kc, sub, n_blocks, M, num_rbf)
     else:
+        sblk = torch.div(g.col.long(), R, rounding_mode="floor")
+        grp = torch.where(sub >= 0, sblk * M + sub.long(), torch.full_like(sblk, n_groups)).to(torch.int32)
         order, grp_ptr = _sorted_by_group(kc, grp, n_groups, num_rbf)
-    eid = torch.arange(E, device=dev, dtype=torch.int32)
-    rec = torch.stack([g.edge_row, (g.row_xoff[row] + col).to(torch.int32), (col - sblk * R).to(torch.int32), eid], 1).contiguous()
     grp_mod = torch.arange(M, device=dev).repeat(n_blocks)
-    grp_tile, tile_info, erec, n_tiles, window = _tiles(order, kc, grp_ptr, n_groups, num_rbf, rec, grp_mod)
+    grp_tile, tile_info, erec, n_tiles, window, n_live = _tiles(order, kc, grp_ptr, n_groups, num_rbf, rec, grp_mod)
     blk_tile = grp_tile[::M].contiguous()
-    plan = TilePlan("src", blk_info, blk_tile, tile_info, erec, n_blocks, n_tiles, bool((~live).any().item()) if E else False)
+    plan = TilePlan("src", blk_info, blk_tile, tile_info, erec, n_blocks, n_tiles, n_live < E)
     plan.window = window
     if _interleave() and n_blocks > 1 and len(g.type_ptr) > 2:       # same idea for the source blocks (consecutive internal atoms)
         tp = torch.tensor(g.type_ptr, dtype=torch.double)

@@ -218,6 +218,12 @@ int64_t hn_tc_split_weights_elems(int32_t n_modules, int32_t hidden, int32_t num
 int hn_tc_split_weights(const float *Wt, int32_t n_modules, int32_t num_rbf, int32_t hidden, void *wsplit /*fp16*/,
                         float *wscale /*[M]*/, void *stream);
 int hn_tc_basis_index(const float *geom, int64_t n_edges, float inv_rc, int32_t num_rbf, int32_t *kc /*[E]*/, void *stream);
+/* Per-edge inputs of a plan in one pass: kc[e] = basis index of the edge (as hn_tc_basis_index), rec[e][4] = its record
+ * (dst-major: xh row, source, row-local index = atom_local[row / rows_per_atom], edge id; src-major: destination row, xh row,
+ * source % src_block, edge id), sub[e] = sort sub-key (dst-major: 0, src-major: sub-network of the row; -1 = inactive row). */
+int hn_tc_plan_records(int32_t src_major, const int32_t *edge_row, const int32_t *col, const int64_t *row_xoff, const int32_t *row_mod,
+                       const int32_t *atom_local, int32_t rows_per_atom, int32_t src_block, const float *geom, float inv_rc,
+                       int32_t num_rbf, int64_t n_edges, int32_t *rec, int32_t *kc, int32_t *sub, void *stream);
 /* Segment-local sort of the plan builder: segment s = entries in_ptr[s] .. in_ptr[s+1] of the edge list `ids` (NULL: identity)
  * -- the CSR entries of a destination block or the transposed-CSR entries of a source block; entries are ordered by (sub, kc)
  * inside their segment (sub: NULL = 0; -1 drops the entry), stable and deterministic.  Count pass: counts[s * n_sub + sub]

@@ -282,6 +282,22 @@ def _tc_tiles_of_group(ks, K, W=32):
     return starts
 
 
+def tc_plan_records(g, geom, inv_rc, num_rbf, src_major, atom_local, src_block):
+    row, col = g.edge_row.long(), g.col.long()
+    m = g.row_mod.long()[row]
+    xr = (g.row_xoff[row] + col).to(torch.int32)
+    eid = torch.arange(g.n_edges, dtype=torch.int32)
+    kc = tc_basis_index(geom, inv_rc, num_rbf)
+    if src_major:
+        rec = torch.stack([g.edge_row, xr, (col % src_block).to(torch.int32), eid], 1)
+        sub = m.to(torch.int32)
+    else:
+        atom = torch.div(row, g.rows_per_atom, rounding_mode="floor")
+        rec = torch.stack([xr, g.col, atom_local[atom].to(torch.int32), eid], 1)
+        sub = torch.where(m >= 0, torch.zeros_like(m), torch.full_like(m, -1)).to(torch.int32)
+    return rec.contiguous(), kc, sub.contiguous()
+
+
 def tc_plan_sort(in_ptr, ids, kc, sub, n_seg, n_sub, num_rbf):
     ip = in_ptr.tolist()
     order, counts = [], torch.zeros(n_seg * n_sub, dtype=torch.int32)
@@ -564,7 +580,7 @@ def install(monkeypatch):
                  "painn_edge_bwd_src", "painn_edge_bwd_w", "gemm_tf32x3_ex", "node_pre", "node_mid", "node_post",
                  "node_post_bwd", "node_mid_bwd", "node_pre_bwd", "gather_rows", "segment_sum", "gemm_tf32x3", "split_tf32",
                  "tc_supported", "tc_block_rows", "tc_groups", "tc_split_weights", "tc_basis_index", "tc_plan_count", "tc_plan_fill",
-                 "tc_plan_sort", "tc_plan_finalize", "tc_tile_windows", "tc_edge_fwd", "tc_edge_bwd_dst", "tc_edge_bwd_src", "readout_fwd", "readout_bwd"):
+                 "tc_plan_records", "tc_plan_sort", "tc_plan_finalize", "tc_tile_windows", "tc_edge_fwd", "tc_edge_bwd_dst", "tc_edge_bwd_src", "readout_fwd", "readout_bwd"):
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(ops, "require_cuda", lambda t, what: None)
     monkeypatch.setattr(ops, "compute_device", lambda t: t.device)
