@@ -24,6 +24,14 @@ namespace {
 
 constexpr int BM = 128, BK = 32;
 
+// measurement switches for A/B builds (profiles/scripts/gemm_ab.sh); 0 = the product
+#ifndef HN_GEMM_AB
+#define HN_GEMM_AB 0      // 1: no operand split, 2: no epilogue math / stores, 3: no MMAs
+#endif
+#ifndef HN_GEMM_STAGES
+#define HN_GEMM_STAGES 3
+#endif
+
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -85,24 +93,24 @@ __device__ __forceinline__ float dssilu(float z) {
 template <int BN>
 struct Smem {
     // three operand stages in flight (with two, the tensor pipe sat at 36 %: every K-chunk waited a full TMA round trip)
-    static constexpr int kStages = 3;
+    static constexpr int kStages = HN_GEMM_STAGES;
     static constexpr int kA = BM * BK * 4;   // 16 KB
     static constexpr int kB = BN * BK * 4;
     static constexpr int kStage = 2 * kA + 2 * kB;
-    static constexpr int kStaging = kStages * kStage;          // 2 x 16 KB: C double-buffered, or (C, C2) single-buffered
+    static constexpr int kStaging = kStages * kStage;          // 2 x 16 KB: one staging tile per epilogue group
     static constexpr int kBars = kStaging + 2 * 16384;
     static constexpr int kTotal = kBars + 256 + 1024;   // barriers + tmem slot, + slack for 1024-byte alignment
 };
 
-// Persistent CTA (one per SM), 384 threads, tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (n-tile fastest):
+// Persistent CTA (one per SM), 512 threads, tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (n-tile fastest):
 //   warp 0    : TMA producer (A raw, W_hi, W_lo K-chunks of 32 floats = one 128-byte swizzle row) into a stage ring
 //   warp 1    : MMA issuer (one thread); accumulators double-buffered in TMEM (2 x BN columns)
 //   warp 2    : TMEM allocation
 //   warps 4-7 : split A in place (hi) + side buffer (lo)
-//   warps 8-11: epilogue of the PREVIOUS tile while the next one is loaded and multiplied:
-//               tcgen05.ld -> +bias / activation -> swizzled staging tile in smem -> TMA store
+//   warps 8-15: epilogue of the PREVIOUS tile while the next one is loaded and multiplied (two groups of four warps, each
+//               with its own staging tile): tcgen05.ld -> +bias / activation -> swizzled staging tile in smem -> TMA store
 template <int BN>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(512, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                    const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmC,
                    const __grid_constant__ CUtensorMap tmC2, const float *__restrict__ bias, float *__restrict__ C,
@@ -131,7 +139,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull0 + 8 * a, 1);
-            mbar_init(tempty0 + 8 * a, 1);
+            mbar_init(tempty0 + 8 * a, 8);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -181,7 +189,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     const uint32_t st = base + s * L::kStage;
                     const uint32_t a_hi = st, a_lo = st + L::kA, b_hi = st + 2 * L::kA, b_lo = b_hi + L::kB;
 #pragma unroll
-                    for (int k4 = 0; k4 < BK / 8; ++k4) {
+                    for (int k4 = 0; k4 < (HN_GEMM_AB == 3 ? 0 : BK / 8); ++k4) {
                         const uint32_t off = k4 * 32;   // 8 tf32 = 32 bytes inside the 128-byte swizzle row
                         umma_tf32(tacc, umma_desc(a_hi + off), umma_desc(b_hi + off), idesc, (kb | k4) != 0);
                         umma_tf32(tacc, umma_desc(a_hi + off), umma_desc(b_lo + off), idesc, 1);
@@ -204,7 +212,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 float4 *hi = reinterpret_cast<float4 *>(gen + s * L::kStage);
                 float4 *lo = reinterpret_cast<float4 *>(gen + s * L::kStage + L::kA);
 #pragma unroll
-                for (int i = 0; i < L::kA / 16 / 128; ++i) {
+                for (int i = 0; i < (HN_GEMM_AB == 1 ? 0 : L::kA / 16 / 128); ++i) {
                     const float4 v = hi[t + i * 128];
                     float4 h, l;
                     h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
@@ -219,24 +227,33 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             }
         }
     } else if (warp >= 8) {
-        // epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 = output rows m0 + 32*(w%4) + lane.  A 32-column chunk of the
-        // tile is staged in shared memory in the 128-byte-swizzle layout and written with one TMA store -- full 128-byte
-        // lines, rows beyond M clipped -- instead of 16-byte scattered stores, one row per thread.
-        const int t = threadIdx.x - 256;
+        // epilogue: two groups of four warps; warp w owns TMEM lanes 32*(w%4) .. +31 = output rows m0 + 32*(w%4) + lane, group
+        // g = (w-8)/4 takes the 32-column chunks g, g+2, ... of the tile (one chunk: tcgen05.ld -> bias / activation -> a
+        // 16 KB staging tile in the 128-byte-swizzle layout -> ONE TMA store: full 128-byte lines, rows beyond M clipped).
+        // Two groups because a chunk is a serial chain (TMEM load, the pre-activation load of mode 2, MUFU, the staging
+        // barriers, the wait for the previous store to have left the staging tile): with one group the epilogue, not the
+        // tensor pipe or HBM, set the tile time of every GEMM with K <= 384 (profiles/r2: A/B without epilogue 5.2 -> 3.0 ms).
+        const int t = (threadIdx.x - 256) & 127;
+        const int grp = (threadIdx.x - 256) >> 7;
         const int q = warp & 3;
         const int rl = q * 32 + lane;                     // row inside the tile
         const bool two = (mode == 1 && C2 != nullptr);
-        uint8_t *stg = gen + L::kStaging;
-        int buf = 0;
+        uint8_t *sC = gen + L::kStaging + grp * 16384;    // one staging tile per group
+        const int bar_id = 1 + grp;
         long long it = 0;
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int n0 = (int)(tile % n_tiles_n) * BN, m0 = (int)(tile / n_tiles_n) * BM;
             const long long row = (long long)m0 + rl;
             const int a = (int)(it & 1);
+            float4 z[8];
+            if (mode == 2 && row < M) {         // pre-activations of the group's first chunk: in flight while the tile is multiplied
+#pragma unroll
+                for (int j = 0; j < 8; ++j) z[j] = __ldg(reinterpret_cast<const float4 *>(aux + row * ld_aux + n0 + grp * 32 + 4 * j));
+            }
             mbar_wait(tfull0 + 8 * a, (uint32_t)((it >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = grp * 32; c0 < BN; c0 += 64) {
                 uint32_t r[32];
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + c0);
                 asm volatile(
@@ -248,52 +265,71 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                       "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (c0 + 32 >= BN) {       // accumulator fully read: hand it back to the MMA warp
+                if (c0 + 64 >= BN) {       // this warp has read its share of the accumulator: hand it back to the MMA warp
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    asm volatile("bar.sync 2, 128;" ::: "memory");
-                    if (t == 0) mbar_arrive(tempty0 + 8 * a);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(tempty0 + 8 * a);            // (8 arrivals = all epilogue warps)
                 }
-                // one output: the two 16 KB staging buffers alternate (the TMA store that read this one two chunks ago must be
-                // done reading); two outputs (mode 1 with C2): one buffer each, the previous chunk's stores must be done
-                uint8_t *sC = two ? stg : stg + buf * 16384, *sC2 = stg + 16384;
-                if (t == 0) {
-                    if (two) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(0) : "memory");
-                    else asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(1) : "memory");
-                }
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (HN_GEMM_AB == 2) continue;
+                float4 o[8];
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 o = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                           __uint_as_float(r[j + 3]));
+                for (int j = 0; j < 8; ++j) {
+                    o[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                       __uint_as_float(r[4 * j + 3]));
                     if (bias != nullptr) {
-                        const float4 b = __ldg(reinterpret_cast<const float4 *>(bias + n0 + c0 + j));
-                        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                        const float4 b = __ldg(reinterpret_cast<const float4 *>(bias + n0 + c0 + 4 * j));
+                        o[j].x += b.x; o[j].y += b.y; o[j].z += b.z; o[j].w += b.w;
                     }
-                    const int sw = rl * 128 + ((((j >> 2) ^ (rl & 7))) << 4);      // 128-byte swizzle: chunk ^= row % 8
-                    if (mode == 1) {          // C2 = pre-activation (optional), C = ScaledSiLU(pre)   (rmnet.py:110-117)
-                        if (two) *reinterpret_cast<float4 *>(sC2 + sw) = o;
-                        o.x = ssilu(o.x); o.y = ssilu(o.y); o.z = ssilu(o.z); o.w = ssilu(o.w);
-                    } else if (mode == 2) {   // C = acc * ScaledSiLU'(aux): backward through the activation
-                        if (row < M) {
-                            const float4 z = __ldg(reinterpret_cast<const float4 *>(aux + row * ld_aux + n0 + c0 + j));
-                            o.x *= dssilu(z.x); o.y *= dssilu(z.y); o.z *= dssilu(z.z); o.w *= dssilu(z.w);
+                }
+                // the TMA store that read the staging tile last must be done reading it
+                if (t == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(0) : "memory");
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                if (two) {                // C2 = pre-activation first, through the same staging tile
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4 *>(sC + rl * 128 + ((j ^ (rl & 7)) << 4)) = o[j];   // 128-byte swizzle: chunk ^= row % 8
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                    if (t == 0) {
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmC2),
+                                     "r"(smem_u32(sC)), "r"(n0 + c0), "r"(m0)
+                                     : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+                if (mode == 1) {          // C = ScaledSiLU(pre)   (rmnet.py:110-117)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        o[j].x = ssilu(o[j].x); o[j].y = ssilu(o[j].y); o[j].z = ssilu(o[j].z); o[j].w = ssilu(o[j].w);
+                    }
+                } else if (mode == 2) {   // C = acc * ScaledSiLU'(aux): backward through the activation
+                    if (row < M) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            o[j].x *= dssilu(z[j].x); o[j].y *= dssilu(z[j].y); o[j].z *= dssilu(z[j].z); o[j].w *= dssilu(z[j].w);
+                        }
+                        if (c0 + 64 < BN) {     // next chunk's pre-activations
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                z[j] = __ldg(reinterpret_cast<const float4 *>(aux + row * ld_aux + n0 + c0 + 64 + 4 * j));
                         }
                     }
-                    *reinterpret_cast<float4 *>(sC + sw) = o;
                 }
+                if (two) {
+                    if (t == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(0) : "memory");
+                    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<float4 *>(sC + rl * 128 + ((j ^ (rl & 7)) << 4)) = o[j];
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> TMA reads
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
                 if (t == 0) {
                     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmC),
                                  "r"(smem_u32(sC)), "r"(n0 + c0), "r"(m0)
                                  : "memory");
-                    if (two)
-                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmC2),
-                                     "r"(smem_u32(sC2)), "r"(n0 + c0), "r"(m0)
-                                     : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
-                buf ^= 1;
             }
         }
         if (t == 0) asm volatile("cp.async.bulk.wait_group %0;" ::"n"(0) : "memory");   // writes complete before exit
@@ -353,7 +389,7 @@ int launch(const float *A, int64_t M, int64_t K, int64_t lda, const float *Whi, 
     const long long tiles = (N / BN) * ((M + BM - 1) / BM);
     const int sms = hn::num_sms() > 0 ? hn::num_sms() : 148;
     dim3 grid((unsigned)(tiles < sms ? tiles : sms));
-    gemm_tf32x3_kernel<BN><<<grid, 384, Smem<BN>::kTotal, st>>>(ta, tbh, tbl, tc, tc2, bias, C, (int)M, (int)N, (int)K, (long long)ldc, mode, aux,
+    gemm_tf32x3_kernel<BN><<<grid, 512, Smem<BN>::kTotal, st>>>(ta, tbh, tbl, tc, tc2, bias, C, (int)M, (int)N, (int)K, (long long)ldc, mode, aux,
                                                                  (long long)ld_aux, C2, (long long)ldc2);
     return hn::check_launch(where);
 }

@@ -177,6 +177,106 @@ extern "C" int hn_node_pre_bwd(int64_t n, int32_t F, const float *g_xn, const fl
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Row normalisation of the node features (the nn.LayerNorm of rmnet.py:39,52 without its affine part, which the caller
+// folds into the first Linear of x_proj):  xhat = (x - mean) * rstd,  rstd = 1 / sqrt(var + eps)  (biased variance).
+// Warp per row, the row lives in registers (F <= 512), two-pass variance; HBM-bound: 8 F bytes per row.
+// Backward:  g_x = rstd * (g - mean(g) - xhat * mean(g * xhat)).
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int kLnMax = 16;     // F / 32 values per lane
+
+template <bool BWD>
+__global__ void __launch_bounds__(256) layernorm_kernel(long long n, int F, float eps, const float *__restrict__ x,
+                                                        const float *__restrict__ g, float *__restrict__ mean_io,
+                                                        float *__restrict__ rstd_io, float *__restrict__ out) {
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= n) return;
+    const int lane = threadIdx.x & 31, nv = F >> 7;          // float4 per lane (F % 128 == 0) ...
+    const int tail = (F & 127) >> 5;                          // ... + scalars per lane for the rest
+    const float *xr = x + row * F;
+    float v[kLnMax], gv[kLnMax];
+    int cnt = 0;
+    for (int i = 0; i < nv; ++i) {
+        const float4 q = __ldg(reinterpret_cast<const float4 *>(xr) + i * 32 + lane);
+        v[cnt] = q.x; v[cnt + 1] = q.y; v[cnt + 2] = q.z; v[cnt + 3] = q.w;
+        if (BWD) {
+            const float4 h = __ldg(reinterpret_cast<const float4 *>(g + row * F) + i * 32 + lane);
+            gv[cnt] = h.x; gv[cnt + 1] = h.y; gv[cnt + 2] = h.z; gv[cnt + 3] = h.w;
+        }
+        cnt += 4;
+    }
+    for (int i = 0; i < tail; ++i) {
+        v[cnt] = __ldg(xr + nv * 128 + i * 32 + lane);
+        if (BWD) gv[cnt] = __ldg(g + row * F + nv * 128 + i * 32 + lane);
+        ++cnt;
+    }
+    const float inv_f = 1.f / (float)F;
+    float mean, rstd;
+    if (!BWD) {
+        float s = 0.f;
+        for (int i = 0; i < cnt; ++i) s += v[i];
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        mean = s * inv_f;
+        float q = 0.f;
+        for (int i = 0; i < cnt; ++i) q += (v[i] - mean) * (v[i] - mean);
+        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        rstd = 1.f / sqrtf(q * inv_f + eps);
+        if (lane == 0) { mean_io[row] = mean; rstd_io[row] = rstd; }
+        for (int i = 0; i < cnt; ++i) v[i] = (v[i] - mean) * rstd;
+    } else {
+        mean = __ldg(mean_io + row);
+        rstd = __ldg(rstd_io + row);
+        float s = 0.f, q = 0.f;
+        for (int i = 0; i < cnt; ++i) {
+            v[i] = (v[i] - mean) * rstd;
+            s += gv[i];
+            q += gv[i] * v[i];
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            q += __shfl_xor_sync(0xffffffffu, q, o);
+        }
+        s *= inv_f; q *= inv_f;
+        for (int i = 0; i < cnt; ++i) v[i] = rstd * (gv[i] - s - v[i] * q);
+    }
+    float *orow = out + row * F;
+    cnt = 0;
+    for (int i = 0; i < nv; ++i) {
+        reinterpret_cast<float4 *>(orow)[i * 32 + lane] = make_float4(v[cnt], v[cnt + 1], v[cnt + 2], v[cnt + 3]);
+        cnt += 4;
+    }
+    for (int i = 0; i < tail; ++i) orow[nv * 128 + i * 32 + lane] = v[cnt++];
+}
+
+int check_ln(const char *where, int64_t n, int32_t F) {
+    HN_REQUIRE(n >= 0, where, "negative row count");
+    HN_REQUIRE(F >= 32 && F % 32 == 0 && F <= 32 * kLnMax, where, "hidden must be a multiple of 32, at most 512");
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int hn_layernorm_fwd(const float *x, int64_t n, int32_t hidden, float eps, float *xhat, float *mean, float *rstd,
+                                void *stream) {
+    const char *where = "hn_layernorm_fwd";
+    if (int rc = check_ln(where, n, hidden)) return rc;
+    if (n == 0) return 0;
+    layernorm_kernel<false><<<(unsigned)((n + 7) / 8), 256, 0, (cudaStream_t)stream>>>(n, hidden, eps, x, nullptr, mean, rstd, xhat);
+    return hn::check_launch(where);
+}
+
+extern "C" int hn_layernorm_bwd(const float *g_xhat, const float *x, const float *mean, const float *rstd, int64_t n,
+                                int32_t hidden, float *g_x, void *stream) {
+    const char *where = "hn_layernorm_bwd";
+    if (int rc = check_ln(where, n, hidden)) return rc;
+    if (n == 0) return 0;
+    layernorm_kernel<true><<<(unsigned)((n + 7) / 8), 256, 0, (cudaStream_t)stream>>>(n, hidden, 0.f, x, g_xhat, const_cast<float *>(mean),
+                                                                                      const_cast<float *>(rstd), g_x);
+    return hn::check_launch(where);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Readout MLP (hermnet.py:112-116,129):  e_i = W2 . ssilu(W1 x_i + b1) + b2  with  W1 [H, F], H = F/2, in plain fp32 FMAs.
 // The per-atom energies are a strongly cancelling sum, so this one small layer (N x F x F/2 FLOP) does not go through the
 // 3xTF32 tensor-core GEMM: measured on the C4 cut-out check |dE|/|E| 7.1e-6 -> 5.1e-6.  Warp per atom; W1 lives in shared

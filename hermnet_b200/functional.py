@@ -310,7 +310,8 @@ class _XProjHV(Function):
     def forward(ctx, x, mods, eps):
         N, F = x.shape
         M = len(mods)
-        xhat, mean, rstd = torch.native_layer_norm(x, (F,), None, None, eps)
+        x = x.contiguous()
+        xhat, mean, rstd = ops.layernorm_fwd(x, eps)
         w1, b1, w1_hi, w1_lo, w1t_hi, w1t_lo = _xproj_folded(mods)
         hpre = torch.empty((N, M * F), dtype=x.dtype, device=x.device)
         h = torch.empty_like(hpre)
@@ -337,7 +338,7 @@ class _XProjHV(Function):
                                aux=hpre[:, m * F:(m + 1) * F])
         hi, lo = ctx.w1t                                                      # [F, M*F]
         g_xhat = ops.gemm_tf32x3_ex(g_pre, hi, lo, None)
-        g_x = torch.ops.aten.native_layer_norm_backward(g_xhat, x, [F], mean, rstd, None, None, [True, False, False])[0]
+        g_x = ops.layernorm_bwd(g_xhat, x, mean, rstd)
         return g_x, None, None
 
 

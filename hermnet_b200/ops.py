@@ -340,6 +340,31 @@ def gather_rows(X: Tensor, idx: Tensor) -> Tensor:
     return out
 
 
+def layernorm_fwd(x: Tensor, eps: float):
+    """``(xhat, mean [n], rstd [n])`` of the affine-free LayerNorm over the last dimension (``hn_layernorm_fwd``)."""
+    lib = _lib.load()
+    dev = _chk("layernorm_fwd", x)
+    _f32("layernorm_fwd", x)
+    n, F = x.shape
+    xhat = torch.empty_like(x)
+    mean = torch.empty(n, dtype=torch.float32, device=dev)
+    rstd = torch.empty(n, dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev), _timed("node_elementwise", dev):
+        _lib.check(lib.hn_layernorm_fwd(_ptr(x), n, F, float(eps), _ptr(xhat), _ptr(mean), _ptr(rstd), _stream(dev)), "hn_layernorm_fwd")
+    return xhat, mean, rstd
+
+
+def layernorm_bwd(g_xhat: Tensor, x: Tensor, mean: Tensor, rstd: Tensor) -> Tensor:
+    lib = _lib.load()
+    dev = _chk("layernorm_bwd", g_xhat, x, mean, rstd)
+    _f32("layernorm_bwd", g_xhat, x, mean, rstd)
+    n, F = x.shape
+    g_x = torch.empty_like(x)
+    with torch.cuda.device(dev), _timed("node_elementwise", dev):
+        _lib.check(lib.hn_layernorm_bwd(_ptr(g_xhat), _ptr(x), _ptr(mean), _ptr(rstd), n, F, _ptr(g_x), _stream(dev)), "hn_layernorm_bwd")
+    return g_x
+
+
 def readout_fwd(x: Tensor, W1: Tensor, b1: Tensor, W2: Tensor, b2: Tensor) -> Tensor:
     """``e_atom [N,1] = W2 . ssilu(W1 x + b1) + b2`` in plain fp32 (hn_readout_fwd)."""
     lib = _lib.load()

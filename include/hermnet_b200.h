@@ -266,6 +266,15 @@ int hn_segment_sum(const float *Y, const int32_t *rowptr, const int32_t *perm, i
                    float *out, void *workspace, int64_t workspace_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Row normalisation of the node features: the nn.LayerNorm of rmnet.py:39,52 without its affine part (the caller folds
+ * weight / bias into the Linear that follows).  xhat[i] = (x[i] - mean[i]) * rstd[i], rstd = 1/sqrt(var + eps), biased
+ * variance over the `hidden` channels; hidden % 32 == 0, <= 512.  Backward: g_x from g_xhat and the saved x, mean, rstd.
+ * ------------------------------------------------------------------------------------------- */
+int hn_layernorm_fwd(const float *x, int64_t n, int32_t hidden, float eps, float *xhat, float *mean, float *rstd, void *stream);
+int hn_layernorm_bwd(const float *g_xhat, const float *x, const float *mean, const float *rstd, int64_t n, int32_t hidden,
+                     float *g_x, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Readout MLP (hermnet.py:112-116,129): e_atom[i] = W2 . ssilu(W1 x[i] + b1) + b2, W1 [F/2, F], W2 [F/2], plain fp32 FMAs
  * (the atomic energies cancel strongly in the sum; this layer does not use the 3xTF32 GEMM).  bwd: g_x[i] = dE/dx[i] given
  * g_e[i] = dL/de_atom[i]; the hidden activations are recomputed.  F = 64 or 128 (W1 lives in shared memory); b2: device

@@ -1,0 +1,13 @@
+#!/bin/bash
+# node-side change check: GEMM / fused-node tests, per-shape GEMM timing, bench line
+cd "$GRAFT_REPO_ROOT"
+mkdir -p gpurun_out
+timeout 300 python -m pytest tests/test_gpu_gemm.py tests/test_fused_node.py -m gpu -x -q 2>&1 | tail -3
+timeout 200 python profiles/gemm_time.py 10 2>&1 | tail -12 | tee gpurun_out/gemm_time.log
+timeout 600 python bench.py --no-cpu-baseline > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err
+python - <<PY
+import json
+d = json.load(open("gpurun_out/bench_quick.json"))
+print("C4 ms/step", d["ms_per_step"], "eager", d["ms_per_step_eager"], "e2e", d["e2e"]["ms_per_step"], "parity", d["parity"]["rel_dE"], d["parity"]["max_dF"])
+print({k: round(v["avg_ms"] * v["launches"] / d["steps"], 2) for k, v in d["kernels"].items()})
+PY

@@ -466,6 +466,18 @@ def tc_edge_bwd_src(p, plan, xh, vec, geom, wsplit, wscale, bias, offset, g_dx, 
     return grad_xh, grad_vec
 
 
+def layernorm_fwd(x, eps):
+    mean = x.mean(1)
+    var = ((x - mean[:, None]) ** 2).mean(1)
+    rstd = 1.0 / torch.sqrt(var + eps)
+    return (x - mean[:, None]) * rstd[:, None], mean, rstd
+
+
+def layernorm_bwd(g_xhat, x, mean, rstd):
+    xhat = (x - mean[:, None]) * rstd[:, None]
+    return rstd[:, None] * (g_xhat - g_xhat.mean(1, keepdim=True) - xhat * (g_xhat * xhat).mean(1, keepdim=True))
+
+
 def readout_fwd(x, W1, b1, W2, b2):
     h = x @ W1.t() + b1
     return (_ssilu(h) @ W2.reshape(-1, 1)) + b2
@@ -580,7 +592,7 @@ def install(monkeypatch):
                  "painn_edge_bwd_src", "painn_edge_bwd_w", "gemm_tf32x3_ex", "node_pre", "node_mid", "node_post",
                  "node_post_bwd", "node_mid_bwd", "node_pre_bwd", "gather_rows", "segment_sum", "gemm_tf32x3", "split_tf32",
                  "tc_supported", "tc_block_rows", "tc_groups", "tc_split_weights", "tc_basis_index", "tc_plan_count", "tc_plan_fill",
-                 "tc_plan_records", "tc_plan_sort", "tc_plan_finalize", "tc_tile_windows", "tc_edge_fwd", "tc_edge_bwd_dst", "tc_edge_bwd_src", "readout_fwd", "readout_bwd"):
+                 "tc_plan_records", "tc_plan_sort", "tc_plan_finalize", "tc_tile_windows", "tc_edge_fwd", "tc_edge_bwd_dst", "tc_edge_bwd_src", "layernorm_fwd", "layernorm_bwd", "readout_fwd", "readout_bwd"):
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(ops, "require_cuda", lambda t, what: None)
     monkeypatch.setattr(ops, "compute_device", lambda t: t.device)

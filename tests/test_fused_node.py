@@ -95,3 +95,23 @@ def test_readout_kernels_match_float64(F):
     (gd,) = torch.autograd.grad((ed * ge.double()).sum(), xd)
     assert float((e.squeeze(1).double() - ed).abs().max()) < 2e-6 * max(1.0, float(ed.abs().max()))
     assert float((gx.double() - gd).abs().max()) < 2e-6 * max(1.0, float(gd.abs().max()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,F", [(1, 128), (1000, 128), (777, 64), (4099, 96), (513, 256), (300, 512)])
+def test_layernorm_kernels_match_float64(n, F):
+    """hn_layernorm_{fwd,bwd} (the affine-free nn.LayerNorm of rmnet.py:39,52) against float64 autograd."""
+    from hermnet_b200 import ops
+    g = torch.Generator().manual_seed(n + F)
+    x = (torch.randn(n, F, generator=g) * torch.exp(torch.randn(n, 1, generator=g)) + torch.randn(n, 1, generator=g)).cuda()
+    gy = torch.randn(n, F, generator=g).cuda()
+    xd = x.double().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xd, (F,), None, None, 1e-5)
+    (gref,) = torch.autograd.grad(ref, xd, gy.double())
+    xhat, mean, rstd = ops.layernorm_fwd(x, 1e-5)
+    assert float((xhat.double() - ref).abs().max()) < 2e-6 * max(1.0, float(ref.abs().max()))
+    assert torch.allclose(mean.double(), xd.mean(1), rtol=1e-6, atol=1e-6)
+    gx = ops.layernorm_bwd(gy, x, mean, rstd)
+    assert float((gx.double() - gref).abs().max()) < 5e-6 * max(1.0, float(gref.abs().max()))
+    t_hat, t_mean, t_rstd = torch.native_layer_norm(x, (F,), None, None, 1e-5)
+    assert float((xhat - t_hat).abs().max()) < 2e-6 * max(1.0, float(t_hat.abs().max()))

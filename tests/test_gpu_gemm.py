@@ -38,3 +38,37 @@ def test_gemm_strided_input_and_determinism():
     ref = a.double() @ w.double().t()
     assert ((out.double() - ref).abs().max() / ref.abs().max()).item() < 1e-5
     assert torch.equal(out, ops.gemm_tf32x3(a, hi, lo, None))
+
+
+def _ssilu(z):
+    return z * torch.sigmoid(z) / 0.6
+
+
+@pytest.mark.parametrize("M,K,N", [(1000, 128, 512), (4097, 256, 128), (333, 128, 192), (20000, 384, 128), (129, 64, 64)])
+def test_gemm_activation_epilogues(M, K, N):
+    """mode 1 (ScaledSiLU + stored pre-activation) and mode 2 (times ScaledSiLU'(aux)) of hn_gemm_tf32x3_ex, written into
+    column blocks of wider buffers (row-pitched outputs / aux), both tile widths (N % 128 == 0 and N % 64 == 0)."""
+    g = torch.Generator().manual_seed(M + 3 * K + N)
+    a = torch.randn(M, K, generator=g).cuda()
+    w = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    hi, lo = ops.split_tf32(w)
+    pre_ref = a.double() @ w.double().t() + b.double()
+    wide = torch.full((M, N + 64), 7.0, device="cuda")
+    wide2 = torch.full((M, 2 * N), -3.0, device="cuda")
+    out = ops.gemm_tf32x3_ex(a, hi, lo, b, out=wide[:, 64:], mode=1, out2=wide2[:, :N])
+    assert out.data_ptr() == wide[:, 64:].data_ptr()
+    assert ((wide2[:, :N].double() - pre_ref).abs().max() / pre_ref.abs().max()).item() < 1e-5
+    assert ((wide[:, 64:].double() - _ssilu(pre_ref)).abs().max() / pre_ref.abs().max()).item() < 1e-5
+    assert torch.all(wide[:, :64] == 7.0) and torch.all(wide2[:, N:] == -3.0)          # neighbours untouched
+    only = ops.gemm_tf32x3_ex(a, hi, lo, b, mode=1)                                    # without the pre-activation output
+    assert torch.equal(only, wide[:, 64:])
+    # mode 2: (a . w^T) * ScaledSiLU'(aux)
+    aux_wide = torch.randn(M, N + 128, generator=g).cuda()
+    aux = aux_wide[:, 128:]
+    z = aux.double().requires_grad_(True)
+    (dz,) = torch.autograd.grad(_ssilu(z).sum(), z)
+    ref2 = (a.double() @ w.double().t()) * dz
+    out2 = ops.gemm_tf32x3_ex(a, hi, lo, None, mode=2, aux=aux)
+    assert ((out2.double() - ref2).abs().max() / ref2.abs().max()).item() < 1e-5
+    assert torch.equal(out2, ops.gemm_tf32x3_ex(a, hi, lo, None, mode=2, aux=aux))     # deterministic
