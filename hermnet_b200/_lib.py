@@ -74,6 +74,8 @@ SIGNATURES = {
     "hn_node_mid_bwd": (c_int32, [c_int64, c_int32, P, P, P, P, c_int64, P, P]),
     "hn_node_pre_bwd": (c_int32, [c_int64, c_int32, P, P, P, P, P, P, P]),
     "hn_gather_rows": (c_int32, [P, P, c_int64, c_int32, P, P]),
+    "hn_layer0_basis_fwd": (c_int32, [P, P, P, P, P, P, P, c_int32, c_int32, P, P, P]),
+    "hn_layer0_basis_bwd": (c_int32, [P, P, P, P, P, P, P, c_int32, c_int32, P, P, P, P]),
     "hn_layernorm_fwd": (c_int32, [P, c_int64, c_int32, c_float, P, P, P, P]),
     "hn_layernorm_bwd": (c_int32, [P, P, P, P, c_int64, c_int32, P, P]),
     "hn_readout_fwd": (c_int32, [P, P, P, P, P, c_int64, c_int32, P, P]),

@@ -422,6 +422,85 @@ def node_update_hv(x, vec, dx, dvec, g: RowGraph, mods):
     return _NodeUpdateHV.apply(x, vec, dx, dvec, g, mods)
 
 
+def _layer0_weights(xh_tab: Tensor, Wt: Tensor, bias: Tensor, M: int, nz: int, F: int, K: int, KP: int):
+    """``BigA, BigC [M, F, KP]`` of include/hermnet_b200.h (hn_layer0_basis_*): the first-layer filter with the element table of
+    projected source features folded in; column ``z*K + k`` = ``x[m][z][f] * W[m][k][f]``, column ``nz*K + z`` = ``x[m][z][f] * b[m][f]``."""
+    tab = xh_tab.view(M, nz, 3 * F)
+
+    def big(x, W, b):
+        out = torch.zeros((M, F, KP), dtype=x.dtype, device=x.device)
+        out[:, :, :nz * K] = torch.einsum("mzf,mkf->mfzk", x, W).reshape(M, F, nz * K)
+        out[:, :, nz * K:nz * K + nz] = (x * b[:, None, :]).transpose(1, 2)
+        return out
+
+    c2 = 1.0 / math.sqrt(F)
+    return big(tab[:, :, :F], Wt[:, :, :F], bias[:, :F]), big(tab[:, :, 2 * F:] * c2, Wt[:, :, 2 * F:], bias[:, 2 * F:])
+
+
+class _Layer0HV(Function):
+    """Edge side of the FIRST HVNet layer (x = Embedding[Z], vec = 0; hermnet.py:123-124, rmnet.py:55-73) by basis aggregation:
+    per-(destination, source element) sums of the radial basis (``hn_layer0_basis_fwd``: 12 Gaussians x 4 weights per edge instead
+    of 3F channels), then one tensor-core GEMM per destination element and output; the backward mirrors it (GEMMs, then
+    ``hn_layer0_basis_bwd`` -> per-edge geometry gradient).  Frozen parameters only (no gradient for the table / filter)."""
+
+    @staticmethod
+    def forward(ctx, geom, xh_tab, Wt, bias, offset, g0: RowGraph, p0, n_elem: int):
+        F, K, M = int(p0.hidden), int(p0.num_rbf), int(p0.n_modules)
+        KP = ops.layer0_row_len(n_elem, K)
+        geom = geom.contiguous()
+        live = getattr(p0, "live", None)
+        Sa, Sc = ops.layer0_basis_fwd(p0, g0, geom, live, offset, n_elem, KP)
+        bigA, bigC = _layer0_weights(xh_tab.detach(), Wt.detach(), bias.detach(), M, n_elem, F, K, KP)
+        a_hi, a_lo = ops.split_tf32(bigA.view(M * F, KP))
+        c_hi, c_lo = ops.split_tf32(bigC.view(M * F, KP))
+        R = int(p0.n_rows)
+        spans = []
+        for t in range(M):
+            sl = g0.dst_slice(t)
+            if sl.stop - sl.start > 0 and g0.mod_active_host[t]:
+                spans.append((t, sl))
+        covered = sum(sl.stop - sl.start for _, sl in spans)
+        alloc = torch.empty if covered == R else torch.zeros
+        dx = alloc((R, F), dtype=geom.dtype, device=geom.device)
+        dvec = alloc((R, 3, F), dtype=geom.dtype, device=geom.device)
+        for t, sl in spans:
+            n = sl.stop - sl.start
+            w = slice(t * F, (t + 1) * F)
+            ops.gemm_tf32x3_ex(Sa[sl], a_hi[w], a_lo[w], None, out=dx[sl])
+            ops.gemm_tf32x3_ex(Sc[sl].view(3 * n, KP), c_hi[w], c_lo[w], None, out=dvec[sl].view(3 * n, F))
+        ctx.g0, ctx.p0, ctx.spans, ctx.dims, ctx.live = g0, p0, spans, (F, K, M, KP, n_elem), live
+        ctx.save_for_backward(geom, offset, bigA, bigC)
+        return dx, dvec
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_dx, g_dvec):
+        geom, offset, bigA, bigC = ctx.saved_tensors
+        F, K, M, KP, n_elem = ctx.dims
+        g_dx, g_dvec = g_dx.contiguous(), g_dvec.contiguous()
+        R = g_dx.size(0)
+        at_hi, at_lo = ops.split_tf32(bigA.transpose(1, 2).reshape(M * KP, F))
+        ct_hi, ct_lo = ops.split_tf32(bigC.transpose(1, 2).reshape(M * KP, F))
+        gSa = torch.empty((R, KP), dtype=g_dx.dtype, device=g_dx.device)
+        gSc = torch.empty((R, 3, KP), dtype=g_dx.dtype, device=g_dx.device)
+        for t, sl in ctx.spans:
+            n = sl.stop - sl.start
+            w = slice(t * KP, (t + 1) * KP)
+            ops.gemm_tf32x3_ex(g_dx[sl], at_hi[w], at_lo[w], None, out=gSa[sl])
+            ops.gemm_tf32x3_ex(g_dvec[sl].view(3 * n, F), ct_hi[w], ct_lo[w], None, out=gSc[sl].view(3 * n, KP))
+        g_geom = ops.layer0_basis_bwd(ctx.p0, ctx.g0, geom, ctx.live, offset, n_elem, KP, gSa, gSc)
+        return g_geom, None, None, None, None, None, None, None
+
+
+def layer0_fusable(hidden: int, num_rbf: int, n_elem: int) -> bool:
+    """The aggregated first-layer pass needs GEMM-shaped outputs (F % 64 == 0) and a row of sums that fits shared memory."""
+    return hidden % 64 == 0 and ops.layer0_row_len(n_elem, num_rbf) <= 3072
+
+
+def layer0_edge(geom, xh_tab, Wt, bias, offset, g0: RowGraph, p0, n_elem: int):
+    return _Layer0HV.apply(geom, xh_tab, Wt, bias, offset, g0, p0, n_elem)
+
+
 # ----------------------------------------------------------------------------------------------------
 # composite (any-order differentiable) formulation
 # ----------------------------------------------------------------------------------------------------

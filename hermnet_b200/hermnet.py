@@ -69,6 +69,7 @@ class _HermNet(nn.Module):
         self.fused_node = True           # frozen HVNet parameters: fused node-side kernels with hand-written backward
         # readout MLP (hermnet.py:129) in plain fp32 (hn_readout_{fwd,bwd}) instead of the 3xTF32 tensor-core GEMM: N x F x F/2
         # FLOP, negligible time, and the per-atom energies are a cancelling sum -- C4 cut-out check: |dE|/|E| 7.1e-6 -> 5.1e-6
+        self.layer0_basis = True         # first layer of the fused HVNet path: basis aggregation + GEMM (Fn.layer0_edge)
         self.readout_fp32 = True
         self.store_features = False   # write data.x / data.vec back like the reference does (hermnet.py:63-64)
         # None: recompute every layer in the backward pass instead of keeping its activations (torch.utils.checkpoint)
@@ -239,7 +240,12 @@ class _HermNet(nn.Module):
                 p0 = ops.EdgeParams(int(uniq.numel()), p.n_rows, p.n_modules, p.hidden, p.num_rbf, p.env_p, p.inv_rc, p.coeff,
                                     p.variant, p.flags)
                 p0.live = p.live
-                dx, dvec = Fn.painn_edge(xh, vec, geom, Wt, bias, self.radial_basis.rbf.offset, g0, p0, True)
+                if self.layer0_basis and Fn.layer0_fusable(F, self.num_rbf, int(uniq.numel())) and not xh.requires_grad:
+                    # ... and the message sum is linear in per-(destination, source element) sums of the radial basis:
+                    # aggregate the 12-wide Gaussian band per edge, mix channels with one GEMM per destination element
+                    dx, dvec = Fn.layer0_edge(geom, xh, Wt, bias, self.radial_basis.rbf.offset, g0, p0, int(uniq.numel()))
+                else:
+                    dx, dvec = Fn.painn_edge(xh, vec, geom, Wt, bias, self.radial_basis.rbf.offset, g0, p0, True)
             else:
                 xh = Fn.xproj_hv(x, [m.message_layer for m in mods], mods[0].message_layer.x_layernorm.eps)
                 dx, dvec = Fn.painn_edge(xh, vec, geom, Wt, bias, self.radial_basis.rbf.offset, g, p, vec_zero)

@@ -340,6 +340,41 @@ def gather_rows(X: Tensor, idx: Tensor) -> Tensor:
     return out
 
 
+def layer0_row_len(n_elem: int, num_rbf: int) -> int:
+    """Length of a basis-sum row of the first-layer pass: ``n_elem * (K + 1)`` sums, padded to a GEMM-friendly multiple."""
+    pad = int(_os.environ.get("HERMNET_B200_L0_PAD", "128"))
+    return (n_elem * (num_rbf + 1) + pad - 1) // pad * pad
+
+
+def layer0_basis_fwd(p: EdgeParams, g, geom: Tensor, live: Optional[Tensor], offset: Tensor, n_elem: int, kp: int):
+    """``(Sa [R,kp], Sc [R,3,kp])``: per-(destination row, source element) sums of the radial basis (``hn_layer0_basis_fwd``);
+    ``g.col`` holds the element index of every row-edge's source."""
+    lib = _lib.load()
+    dev = _chk("layer0_basis_fwd", g.rowptr, g.col, g.row_mod, geom, live, offset)
+    _i32("layer0_basis_fwd", g.rowptr, g.col, g.row_mod)
+    _f32("layer0_basis_fwd", geom, offset)
+    R = int(p.n_rows)
+    Sa = torch.empty((R, kp), dtype=torch.float32, device=dev)
+    Sc = torch.empty((R, 3, kp), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev), _timed("layer0_basis_fwd", dev):
+        _lib.check(lib.hn_layer0_basis_fwd(ctypes.byref(p), _ptr(g.rowptr), _ptr(g.col), _ptr(g.row_mod), _ptr(geom), _ptr(live),
+                                           _ptr(offset), int(n_elem), int(kp), _ptr(Sa), _ptr(Sc), _stream(dev)), "hn_layer0_basis_fwd")
+    return Sa, Sc
+
+
+def layer0_basis_bwd(p: EdgeParams, g, geom: Tensor, live: Optional[Tensor], offset: Tensor, n_elem: int, kp: int, g_Sa: Tensor,
+                     g_Sc: Tensor) -> Tensor:
+    lib = _lib.load()
+    dev = _chk("layer0_basis_bwd", g.rowptr, g.col, g.row_mod, geom, live, offset, g_Sa, g_Sc)
+    _f32("layer0_basis_bwd", geom, offset, g_Sa, g_Sc)
+    g_geom = torch.empty((geom.size(0), 4), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev), _timed("layer0_basis_bwd", dev):
+        _lib.check(lib.hn_layer0_basis_bwd(ctypes.byref(p), _ptr(g.rowptr), _ptr(g.col), _ptr(g.row_mod), _ptr(geom), _ptr(live),
+                                           _ptr(offset), int(n_elem), int(kp), _ptr(g_Sa), _ptr(g_Sc), _ptr(g_geom), _stream(dev)),
+                   "hn_layer0_basis_bwd")
+    return g_geom
+
+
 def layernorm_fwd(x: Tensor, eps: float):
     """``(xhat, mean [n], rstd [n])`` of the affine-free LayerNorm over the last dimension (``hn_layernorm_fwd``)."""
     lib = _lib.load()

@@ -168,6 +168,27 @@ int hn_painn_edge_bwd_w(const hn_edge_params *p, const float *xh, const float *v
                         void *stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * First-layer edge pass of HVNet by basis aggregation.  In the first layer x = Embedding[Z], vec = 0
+ * (HermNet/hermnet.py:123-124): the projected source features depend only on the source ELEMENT z, so the message sum of
+ * rmnet.py:55-73 is linear in per-(destination, element) sums of the radial basis:
+ *   Sa[r][z*K + k]        = sum_{e -> r, elem[e] = z} env * gauss_k(d_e)          Sa[r][n_elem*K + z]    = edge count
+ *   Sc[r][c][z*K + k]     = sum ... * u_e[c]                                      Sc[r][c][n_elem*K + z] = sum u_e[c]
+ * (rows of `kp` floats, kp % 4 == 0, kp >= n_elem * (K + 1); the pad is written as zeros), and
+ *   dx[r] = [Sa[r]] . BigA[m]^T,  dvec[r][c] = [Sc[r][c]] . BigC[m]^T   with  BigA[m][f][z*K+k] = xa[m][z][f] * W_a[m][k][f],
+ *   BigA[m][f][n_elem*K+z] = xa[m][z][f] * b_a[m][f]  (BigC likewise with xc / sqrt(F)) -- dense GEMMs (hn_gemm_tf32x3).
+ * `elem[e]` = element index of the source of row-edge e; rows with row_mod < 0 are skipped (fwd: their S rows are not
+ * written; bwd: zeros in g_geom).  bwd: g_geom[e] = (dL/du, dL/dd) from g_Sa / g_Sc (same layout as Sa / Sc).
+ * p: n_rows, num_rbf, env_p, inv_rc, coeff, flags (bit 0: `live` [E] uint8 marks the entries of a Verlet-skin list that are
+ * edges right now; else live may be NULL).
+ * ------------------------------------------------------------------------------------------- */
+int hn_layer0_basis_fwd(const hn_edge_params *p, const int32_t *rowptr, const int32_t *elem, const int32_t *row_mod,
+                        const float *geom, const uint8_t *live, const float *offset, int32_t n_elem, int32_t kp,
+                        float *Sa /*[R,kp]*/, float *Sc /*[R,3,kp]*/, void *stream);
+int hn_layer0_basis_bwd(const hn_edge_params *p, const int32_t *rowptr, const int32_t *elem, const int32_t *row_mod,
+                        const float *geom, const uint8_t *live, const float *offset, int32_t n_elem, int32_t kp,
+                        const float *g_Sa, const float *g_Sc, float *g_geom /*[E,4]*/, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Tensor-core PaiNN edge kernels (tcgen05 / TMEM / TMA; hidden_channels == 128, num_rbf <= 256).
  * Same arithmetic and reference lines as hn_painn_edge_* above; the filter projection
  * rbf_proj (HermNet/rmnet.py:45,55) runs as fp16-split (hi + lo) tensor-core tiles with fp32

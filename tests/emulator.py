@@ -466,6 +466,49 @@ def tc_edge_bwd_src(p, plan, xh, vec, geom, wsplit, wscale, bias, offset, g_dx, 
     return grad_xh, grad_vec
 
 
+def _layer0_terms(p, g, geom, live, offset, deriv=False):
+    row = g.edge_row.long()
+    act = g.row_mod.long()[row] >= 0
+    if live is not None and (p.flags & 1):
+        act = act & live.bool()
+    band = _band(p, geom, offset, deriv)
+    w = torch.cat([torch.ones_like(geom[:, :1]), geom[:, :3]], 1)          # weights (1, ux, uy, uz)
+    return row, act, band, w
+
+
+def layer0_basis_fwd(p, g, geom, live, offset, n_elem, kp):
+    K = p.num_rbf
+    row, act, val, w = _layer0_terms(p, g, geom, live, offset)
+    z = g.col.long()
+    S = torch.zeros((p.n_rows, 4, kp), dtype=geom.dtype)
+    a = act.to(geom.dtype)
+    contrib = (w[:, :, None] * val[:, None, :]) * a[:, None, None]         # [E,4,K]
+    flat = S.view(p.n_rows, 4, kp)
+    for zz in range(n_elem):
+        sel = (z == zz)
+        if sel.any():
+            flat[:, :, zz * K:(zz + 1) * K].index_add_(0, row[sel], contrib[sel])
+            cnt = torch.zeros((p.n_rows, 4), dtype=geom.dtype).index_add_(0, row[sel], w[sel] * a[sel, None])
+            flat[:, :, n_elem * K + zz] += cnt
+    return S[:, 0].contiguous(), S[:, 1:].contiguous()
+
+
+def layer0_basis_bwd(p, g, geom, live, offset, n_elem, kp, g_Sa, g_Sc):
+    K = p.num_rbf
+    row, act, (val, dval), w = _layer0_terms(p, g, geom, live, offset, deriv=True)
+    z = g.col.long()
+    G = torch.cat([g_Sa[:, None, :], g_Sc], 1)                              # [R,4,kp]
+    E = geom.size(0)
+    idx = (z[:, None] * K + torch.arange(K)[None, :])                       # [E,K]
+    Ge = G[row]                                                             # [E,4,kp]
+    Gk = torch.gather(Ge, 2, idx[:, None, :].expand(E, 4, K))               # [E,4,K]
+    Gc = torch.gather(Ge, 2, (n_elem * K + z)[:, None, None].expand(E, 4, 1)).squeeze(2)   # [E,4]
+    gd = ((Gk * w[:, :, None]).sum(1) * dval).sum(1)
+    gu = (Gk[:, 1:, :] * val[:, None, :]).sum(2) + Gc[:, 1:]
+    out = torch.cat([gu, gd[:, None]], 1) * act.to(geom.dtype)[:, None]
+    return out.contiguous()
+
+
 def layernorm_fwd(x, eps):
     mean = x.mean(1)
     var = ((x - mean[:, None]) ** 2).mean(1)
@@ -592,7 +635,7 @@ def install(monkeypatch):
                  "painn_edge_bwd_src", "painn_edge_bwd_w", "gemm_tf32x3_ex", "node_pre", "node_mid", "node_post",
                  "node_post_bwd", "node_mid_bwd", "node_pre_bwd", "gather_rows", "segment_sum", "gemm_tf32x3", "split_tf32",
                  "tc_supported", "tc_block_rows", "tc_groups", "tc_split_weights", "tc_basis_index", "tc_plan_count", "tc_plan_fill",
-                 "tc_plan_records", "tc_plan_sort", "tc_plan_finalize", "tc_tile_windows", "tc_edge_fwd", "tc_edge_bwd_dst", "tc_edge_bwd_src", "layernorm_fwd", "layernorm_bwd", "readout_fwd", "readout_bwd"):
+                 "tc_plan_records", "tc_plan_sort", "tc_plan_finalize", "tc_tile_windows", "tc_edge_fwd", "tc_edge_bwd_dst", "tc_edge_bwd_src", "layer0_basis_fwd", "layer0_basis_bwd", "layernorm_fwd", "layernorm_bwd", "readout_fwd", "readout_bwd"):
         monkeypatch.setattr(ops, name, globals()[name])
     monkeypatch.setattr(ops, "require_cuda", lambda t, what: None)
     monkeypatch.setattr(ops, "compute_device", lambda t: t.device)

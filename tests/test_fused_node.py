@@ -115,3 +115,77 @@ def test_layernorm_kernels_match_float64(n, F):
     assert float((gx.double() - gref).abs().max()) < 5e-6 * max(1.0, float(gref.abs().max()))
     t_hat, t_mean, t_rstd = torch.native_layer_norm(x, (F,), None, None, 1e-5)
     assert float((xhat - t_hat).abs().max()) < 2e-6 * max(1.0, float(t_hat.abs().max()))
+
+
+def _run_l0(model, pos, Z, cell, on):
+    model.layer0_basis = on
+    return _run(model, pos, Z, cell, True)
+
+
+@pytest.mark.parametrize("elems,zs,F,K", [(["H", "O"], [1, 8], 64, 32), (["H", "O", "C"], [1, 8, 7], 64, 20)])
+def test_layer0_basis_aggregation_matches_the_edge_kernels_on_cpu_emulation(emu, monkeypatch, elems, zs, F, K):
+    """First layer by basis aggregation + GEMM (functional._Layer0HV) == the element-table edge kernels, values and gradients."""
+    from hermnet_b200 import ops
+    pos, Z, cell = _system(4, zs, 13)
+    model = _model(elems, F, K, "cpu")
+    calls = []
+    real = ops.layer0_basis_fwd
+    monkeypatch.setattr(ops, "layer0_basis_fwd", lambda *a, **k: (calls.append(1), real(*a, **k))[1])
+    e1, f1, c1 = _run_l0(model, pos, Z, cell, True)
+    assert len(calls) == 1
+    e0, f0, c0 = _run_l0(model, pos, Z, cell, False)
+    assert len(calls) == 1
+    assert float((e1 - e0).abs().max()) <= 1e-5 * max(1.0, float(e0.abs().max()))
+    assert float((f1 - f0).abs().max()) <= 1e-4 * max(1.0, float(f0.abs().max()))
+    assert float((c1 - c0).abs().max()) <= 1e-4 * max(1.0, float(c0.abs().max()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("elems,zs,F,K,n_side", [(["Li", "Al", "Si", "O"], [3, 13, 14, 8], 128, 128, 9),
+                                                 (["H", "O", "C"], [1, 8, 7], 64, 20, 7),
+                                                 (["Cr", "Fe"], [24, 26], 256, 64, 6)])
+def test_layer0_basis_aggregation_matches_the_edge_kernels(elems, zs, F, K, n_side):
+    pos, Z, cell = _system(n_side, zs, 17)
+    dev = "cuda:0"
+    model = _model(elems, F, K, dev, layers=2)
+    pos, Z, cell = pos.to(dev), Z.to(dev), cell.to(dev)
+    e1, f1, c1 = _run_l0(model, pos, Z, cell, True)
+    e0, f0, c0 = _run_l0(model, pos, Z, cell, False)
+    assert float((e1 - e0).abs().max()) <= 1e-5 * max(1.0, float(e0.abs().max()))
+    assert float((f1 - f0).abs().max()) <= 1e-4 * max(1.0, float(f0.abs().max()))
+    assert float((c1 - c0).abs().max()) <= 1e-4 * max(1.0, float(c0.abs().max()))
+
+
+@pytest.mark.gpu
+def test_layer0_basis_kernels_match_the_emulation():
+    """hn_layer0_basis_{fwd,bwd} against the torch restatement (tests/emulator.py) on a real graph, with a live mask."""
+    from hermnet_b200 import ops
+    from tests import emulator as E
+    pos, Z, cell = _system(6, [3, 13, 14, 8], 5)
+    dev = "cuda:0"
+    model = _model(["Li", "Al", "Si", "O"], 128, 128, dev)
+    g = model.build_graph(pos.to(dev), Z.to(dev), cell.to(dev))
+    uniq, g0 = model._layer0_tables(g, Z.to(dev)[g.perm])
+    geom = ops.edge_geom_fwd(pos.to(dev)[g.perm].contiguous(), cell.to(dev), g)
+    p = ops.edge_params(g, g.n_modules, 128, 128, int(model.radial_basis.envelope.p), model.rc, model.radial_basis.rbf.coeff)
+    gen = torch.Generator().manual_seed(1)
+    live = (torch.rand(g.n_edges, generator=gen) > 0.2).to(torch.uint8).to(dev)
+    off = model.radial_basis.rbf.offset
+    nz, kp = int(uniq.numel()), ops.layer0_row_len(int(uniq.numel()), 128)
+    cpu = lambda t: t.cpu() if torch.is_tensor(t) else t
+    import copy
+    gc = copy.copy(g0)
+    for k in ("rowptr", "col", "row_mod", "edge_row"):
+        setattr(gc, k, getattr(g0, k).cpu())
+    for flags, lv in ((0, None), (1, live)):
+        p.flags = flags
+        Sa, Sc = ops.layer0_basis_fwd(p, g0, geom, lv, off, nz, kp)
+        Sa_r, Sc_r = E.layer0_basis_fwd(p, gc, geom.cpu(), cpu(lv), off.cpu(), nz, kp)
+        act = (g0.row_mod >= 0).cpu()
+        assert float((Sa.cpu()[act] - Sa_r[act]).abs().max()) < 2e-5 * max(1.0, float(Sa_r.abs().max()))
+        assert float((Sc.cpu()[act] - Sc_r[act]).abs().max()) < 2e-5 * max(1.0, float(Sc_r.abs().max()))
+        gSa = torch.randn(Sa.shape, generator=gen).to(dev)
+        gSc = torch.randn(Sc.shape, generator=gen).to(dev)
+        gg = ops.layer0_basis_bwd(p, g0, geom, lv, off, nz, kp, gSa, gSc)
+        gg_r = E.layer0_basis_bwd(p, gc, geom.cpu(), cpu(lv), off.cpu(), nz, kp, gSa.cpu(), gSc.cpu())
+        assert float((gg.cpu() - gg_r).abs().max()) < 1e-4 * max(1.0, float(gg_r.abs().max()))
