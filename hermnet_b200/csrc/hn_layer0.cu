@@ -94,31 +94,41 @@ __global__ void __launch_bounds__(32 * kWarps) layer0_basis_kernel(L0Args A, flo
     float *s0 = S + (2 * half) * KP, *s1 = s0 + KP;        // the two sums this lane owns: half 0 (1, ux), half 1 (uy, uz)
     for (int eb = e0; eb < e1; eb += 32) {
         const int nb = min(32, e1 - eb);
+        // lane l prepares edge eb + l: everything that only depends on the edge is computed once, then broadcast per edge
         float4 gl = make_float4(0.f, 0.f, 0.f, 0.f);
-        int zl = -1;                                       // -1: no edge (beyond the row, or a dead entry of a Verlet-skin list)
+        float ul = 2.f, envl = 0.f, de1l = 0.f, de0l = 0.f;
+        int zkl = -1;                                      // z | kc << 8;  -1: no edge (beyond the row, or a dead entry of a Verlet-skin list)
         if (lane < nb) {
             gl = __ldg(A.geom + eb + lane);
-            zl = __ldg(A.elem + eb + lane);
-            if (A.live != nullptr && A.live[eb + lane] == 0) zl = -1;
+            const int z = __ldg(A.elem + eb + lane);
+            const bool dead = A.live != nullptr && A.live[eb + lane] == 0;
+            ul = gl.w * A.inv_rc;
+            float env, denv;
+            envelope(fminf(ul, 1.f), A.env_p, env, denv);
+            envl = ul < 1.f ? env : 0.f;
+            de1l = envl * 2.f * A.coeff * A.inv_rc;        // d/dd (env gauss_k) = gauss_k * (de1 * diff + de0)
+            de0l = ul < 1.f ? denv * A.inv_rc : 0.f;
+            const int kc = min((int)(fminf(ul, 1.f) * (float)(K - 1)), K - 1);
+            if (!dead) zkl = z | (kc << 8);
         }
         auto edge = [&](int j, float &w0, float &w1, float &val, float &dval, int &z, int &idx, bool &valid) {
             const float gx = __shfl_sync(0xffffffffu, gl.x, j), gy = __shfl_sync(0xffffffffu, gl.y, j),
-                        gz = __shfl_sync(0xffffffffu, gl.z, j), gd = __shfl_sync(0xffffffffu, gl.w, j);
-            z = __shfl_sync(0xffffffffu, zl, j);
-            const float u = gd * A.inv_rc;
+                        gz = __shfl_sync(0xffffffffu, gl.z, j), u = __shfl_sync(0xffffffffu, ul, j),
+                        env = __shfl_sync(0xffffffffu, envl, j);
+            const int zk = __shfl_sync(0xffffffffu, zkl, j);
+            z = zk < 0 ? -1 : (zk & 255);
             w0 = half == 0 ? 1.f : gy;
             w1 = half == 0 ? gx : gz;
-            float env, denv;
-            envelope(fminf(u, 1.f), A.env_p, env, denv);
-            const int kc = min((int)(fminf(u, 1.f) * (float)(K - 1)), K - 1);
-            const int k = kc - kBandLo + kk;
-            valid = z >= 0 && u < 1.f && kk < kBand && k >= 0 && k < K;
+            const int k = (zk >> 8) - kBandLo + kk;
+            valid = zk >= 0 && u < 1.f && kk < kBand && k >= 0 && k < K;
             const int ks = min(max(k, 0), K - 1);
             const float diff = u - offs[ks];
             float gg;
             asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(gg) : "f"(cl2 * diff * diff));
-            val = valid ? env * gg : 0.f;
-            dval = valid ? gg * fmaf(env * 2.f * A.coeff * A.inv_rc, diff, denv * A.inv_rc) : 0.f;
+            gg = valid ? gg : 0.f;
+            val = env * gg;
+            dval = 0.f;
+            if (BWD) dval = gg * fmaf(__shfl_sync(0xffffffffu, de1l, j), diff, __shfl_sync(0xffffffffu, de0l, j));
             idx = max(z, 0) * K + ks;
         };
         if (!BWD) {
@@ -143,7 +153,7 @@ __global__ void __launch_bounds__(32 * kWarps) layer0_basis_kernel(L0Args A, flo
                     float w0, w1, val, dval;
                     int z, idx;
                     bool valid;
-                    edge(j4 + jj, w0, w1, val, dval, z, idx, valid);      // (lanes >= nb hold zl = -1: all zeros)
+                    edge(j4 + jj, w0, w1, val, dval, z, idx, valid);      // (lanes >= nb hold zkl = -1: all zeros)
                     const float a0 = s0[idx], a1 = s1[idx];
                     acc[4 * jj + 0] = half == 0 ? a1 * val : 0.f;          // dL/dux
                     acc[4 * jj + 1] = half == 0 ? 0.f : a0 * val;          // dL/duy
@@ -152,7 +162,8 @@ __global__ void __launch_bounds__(32 * kWarps) layer0_basis_kernel(L0Args A, flo
                 }
                 const float tot = transpose_reduce16(acc, lane);            // lane & 15 = 4 * jj + component
                 const int jj = kk >> 2, comp = kk & 3;
-                const int zj = __shfl_sync(0xffffffffu, zl, (j4 + jj) & 31);
+                const int zkj = __shfl_sync(0xffffffffu, zkl, (j4 + jj) & 31);
+                const int zj = zkj < 0 ? -1 : (zkj & 255);
                 if (lane < 16 && j4 + jj < nb) {
                     float out = tot;
                     if (comp < 3 && zj >= 0) out += S[(1 + comp) * KP + cnt0 + zj];      // the count (filter-bias) terms
@@ -173,7 +184,7 @@ __global__ void __launch_bounds__(32 * kWarps) layer0_basis_kernel(L0Args A, flo
 int check(const char *where, const hn_edge_params *p, int32_t n_elem, int32_t kp) {
     HN_REQUIRE(p != nullptr, where, "null params");
     HN_REQUIRE(p->n_rows >= 0 && p->num_rbf >= 2 && p->env_p >= 1, where, "bad sizes");
-    HN_REQUIRE(n_elem >= 1 && kp % 4 == 0 && (int64_t)kp >= (int64_t)n_elem * (p->num_rbf + 1), where,
+    HN_REQUIRE(n_elem >= 1 && n_elem <= 255 && kp % 4 == 0 && (int64_t)kp >= (int64_t)n_elem * (p->num_rbf + 1), where,
                "row length must be a multiple of 4 and hold n_elem * (num_rbf + 1) sums");
     HN_REQUIRE((int64_t)kWarps * (4 * kp + 64) * 4 + 4 * (int64_t)p->num_rbf <= 200 * 1024, where, "row too long for shared memory");
     return 0;
