@@ -70,7 +70,9 @@ __global__ void __launch_bounds__(32 * kWarps) layer0_basis_kernel(L0Args A, flo
     __syncthreads();
     const long long row = (long long)blockIdx.x * kWarps + warp;
     if (row >= A.n_rows) return;
-    float *S = offs + koff + (size_t)warp * (4 * KP + 64);
+    // forward: the row's sums live in shared memory (read-modify-write per edge); backward: the g_S row is only read (48 words per
+    // edge out of 4 KP) -- straight from global memory / L1, which leaves the occupancy to the registers
+    float *S = offs + koff + (BWD ? 0 : (size_t)warp * (4 * KP + 64));
     float *scratch = S + 4 * KP + lane;
     const int e0 = __ldg(A.rowptr + row), e1 = __ldg(A.rowptr + row + 1);
     if (__ldg(A.row_mod + row) < 0) {
@@ -79,19 +81,16 @@ __global__ void __launch_bounds__(32 * kWarps) layer0_basis_kernel(L0Args A, flo
         return;
     }
     const int n4 = KP >> 2;
-    if (BWD) {
-        const float4 *ra = reinterpret_cast<const float4 *>(gSa + (size_t)row * KP);
-        const float4 *rc = reinterpret_cast<const float4 *>(gSc + (size_t)row * 3 * KP);
-        for (int i = lane; i < n4; i += 32) reinterpret_cast<float4 *>(S)[i] = __ldg(ra + i);
-        for (int i = lane; i < 3 * n4; i += 32) reinterpret_cast<float4 *>(S)[n4 + i] = __ldg(rc + i);
-    } else {
+    if (!BWD) {
         for (int i = lane; i < 4 * n4 + 16; i += 32) reinterpret_cast<float4 *>(S)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncwarp();
     }
-    __syncwarp();
     const int kk = lane & 15, half = lane >> 4;
     const int cnt0 = A.nz * K;
     const float cl2 = A.coeff * 1.4426950408889634f;
     float *s0 = S + (2 * half) * KP, *s1 = s0 + KP;        // the two sums this lane owns: half 0 (1, ux), half 1 (uy, uz)
+    const float *gc = BWD ? gSc + (size_t)row * 3 * KP : nullptr;
+    const float *g0 = BWD ? (half == 0 ? gSa + (size_t)row * KP : gc + KP) : nullptr, *g1 = BWD ? (half == 0 ? gc : gc + 2 * KP) : nullptr;
     for (int eb = e0; eb < e1; eb += 32) {
         const int nb = min(32, e1 - eb);
         // lane l prepares edge eb + l: everything that only depends on the edge is computed once, then broadcast per edge
@@ -154,7 +153,7 @@ __global__ void __launch_bounds__(32 * kWarps) layer0_basis_kernel(L0Args A, flo
                     int z, idx;
                     bool valid;
                     edge(j4 + jj, w0, w1, val, dval, z, idx, valid);      // (lanes >= nb hold zkl = -1: all zeros)
-                    const float a0 = s0[idx], a1 = s1[idx];
+                    const float a0 = __ldg(g0 + idx), a1 = __ldg(g1 + idx);
                     acc[4 * jj + 0] = half == 0 ? a1 * val : 0.f;          // dL/dux
                     acc[4 * jj + 1] = half == 0 ? 0.f : a0 * val;          // dL/duy
                     acc[4 * jj + 2] = half == 0 ? 0.f : a1 * val;          // dL/duz
@@ -166,7 +165,7 @@ __global__ void __launch_bounds__(32 * kWarps) layer0_basis_kernel(L0Args A, flo
                 const int zj = zkj < 0 ? -1 : (zkj & 255);
                 if (lane < 16 && j4 + jj < nb) {
                     float out = tot;
-                    if (comp < 3 && zj >= 0) out += S[(1 + comp) * KP + cnt0 + zj];      // the count (filter-bias) terms
+                    if (comp < 3 && zj >= 0) out += __ldg(gc + comp * KP + cnt0 + zj);      // the count (filter-bias) terms
                     reinterpret_cast<float *>(g_geom + eb + j4 + jj)[comp] = zj >= 0 ? out : 0.f;
                 }
             }
@@ -202,7 +201,7 @@ int launch(const char *where, const hn_edge_params *p, const int32_t *rowptr, co
     a.offset = offset; a.n_rows = p->n_rows; a.K = p->num_rbf; a.nz = n_elem; a.KP = kp; a.env_p = p->env_p;
     a.inv_rc = p->inv_rc; a.coeff = p->coeff;
     HN_REQUIRE(!(p->flags & 1) || live != nullptr, where, "a Verlet-skin list (flags bit 0) needs the live mask");
-    const size_t smem = ((size_t)kWarps * (4 * kp + 64) + ((p->num_rbf + 3) & ~3)) * sizeof(float);
+    const size_t smem = ((BWD ? 0 : (size_t)kWarps * (4 * kp + 64)) + ((p->num_rbf + 3) & ~3)) * sizeof(float);
     HN_CUDA(cudaFuncSetAttribute(layer0_basis_kernel<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), where);
     const unsigned blocks = (unsigned)((p->n_rows + kWarps - 1) / kWarps);
     layer0_basis_kernel<BWD><<<blocks, 32 * kWarps, smem, (cudaStream_t)stream>>>(a, Sa, Sc, gSa, gSc, reinterpret_cast<float4 *>(g_geom));
