@@ -28,9 +28,13 @@ constexpr int BM = 128, BK = 32;
 #ifndef HN_GEMM_AB
 #define HN_GEMM_AB 0      // 1: no operand split, 2: no epilogue math / stores, 3: no MMAs
 #endif
-#ifndef HN_GEMM_STAGES
-#define HN_GEMM_STAGES 3
+#ifndef HN_GEMM_MT
+#define HN_GEMM_MT 2      // 128-row sub-tiles per CTA tile: they share every W chunk staged in shared memory
 #endif
+#ifndef HN_GEMM_STAGES
+#define HN_GEMM_STAGES (HN_GEMM_MT == 1 ? 3 : 2)
+#endif
+constexpr int MT = HN_GEMM_MT;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -96,15 +100,18 @@ struct Smem {
     static constexpr int kStages = HN_GEMM_STAGES;
     static constexpr int kA = BM * BK * 4;   // 16 KB
     static constexpr int kB = BN * BK * 4;
-    static constexpr int kStage = 2 * kA + 2 * kB;
+    static constexpr int kStage = MT * 2 * kA + 2 * kB;      // per sub-tile A raw -> hi | A lo, then W hi | W lo
     static constexpr int kStaging = kStages * kStage;          // 2 x 16 KB: one staging tile per epilogue group
     static constexpr int kBars = kStaging + 2 * 16384;
     static constexpr int kTotal = kBars + 256 + 1024;   // barriers + tmem slot, + slack for 1024-byte alignment
 };
 
-// Persistent CTA (one per SM), 512 threads, tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (n-tile fastest):
+// Persistent CTA (one per SM), 512 threads, tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... (n-tile fastest).  A tile is
+// MT = 2 sub-tiles of 128 rows x BN columns that share every W chunk staged in shared memory: W (hi + lo) is re-read from L2 for
+// every tile, twice the bytes of the A chunk, and L2 -> SM bandwidth bounded the main loop (ncu: 8.9 TB/s of it at 60 % tensor
+// pipe); with two sub-tiles per W chunk the operand traffic per output row drops by a third.
 //   warp 0    : TMA producer (A raw, W_hi, W_lo K-chunks of 32 floats = one 128-byte swizzle row) into a stage ring
-//   warp 1    : MMA issuer (one thread); accumulators double-buffered in TMEM (2 x BN columns)
+//   warp 1    : MMA issuer (one thread); accumulators double-buffered in TMEM (2 x MT x BN columns)
 //   warp 2    : TMEM allocation
 //   warps 4-7 : split A in place (hi) + side buffer (lo)
 //   warps 8-15: epilogue of the PREVIOUS tile while the next one is loaded and multiplied (two groups of four warps, each
@@ -129,7 +136,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_k = K / BK;
     const int n_tiles_n = N / BN;
-    const long long n_tiles = (long long)n_tiles_n * ((M + BM - 1) / BM);
+    const long long n_tiles = (long long)n_tiles_n * ((M + BM * MT - 1) / (BM * MT));
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -144,7 +151,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        constexpr uint32_t cols = 2 * BN;   // power of two >= 32 (BN in {64, 128})
+        constexpr uint32_t cols = 2 * MT * BN;   // power of two >= 32 (BN in {64, 128}, MT in {1, 2})
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -157,16 +164,17 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (lane == 0) {
             long long kbg = 0;                                  // running K-chunk counter (stage ring position)
             for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int n0 = (int)(tile % n_tiles_n) * BN, m0 = (int)(tile / n_tiles_n) * BM;
+                const int n0 = (int)(tile % n_tiles_n) * BN, m0 = (int)(tile / n_tiles_n) * (BM * MT);
                 for (int kb = 0; kb < num_k; ++kb, ++kbg) {
                     const int s = (int)(kbg % STAGES);
                     const uint32_t ph = (uint32_t)(kbg / STAGES) & 1;
                     mbar_wait(empty0 + 8 * s, ph ^ 1);
                     const uint32_t st = base + s * L::kStage;
-                    mbar_expect_tx(full0 + 8 * s, L::kA + 2 * L::kB);
-                    tma_load_2d(st, &tmA, full0 + 8 * s, kb * BK, m0);
-                    tma_load_2d(st + 2 * L::kA, &tmBhi, full0 + 8 * s, kb * BK, n0);
-                    tma_load_2d(st + 2 * L::kA + L::kB, &tmBlo, full0 + 8 * s, kb * BK, n0);
+                    mbar_expect_tx(full0 + 8 * s, MT * L::kA + 2 * L::kB);
+                    for (int h = 0; h < MT; ++h)      // (rows beyond M: zero-filled by the TMA unit, full box counted)
+                        tma_load_2d(st + h * 2 * L::kA, &tmA, full0 + 8 * s, kb * BK, m0 + h * BM);
+                    tma_load_2d(st + MT * 2 * L::kA, &tmBhi, full0 + 8 * s, kb * BK, n0);
+                    tma_load_2d(st + MT * 2 * L::kA + L::kB, &tmBlo, full0 + 8 * s, kb * BK, n0);
                 }
             }
         }
@@ -178,7 +186,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const int a = (int)(it & 1);
             mbar_wait(tempty0 + 8 * a, (uint32_t)((it >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t tacc = tmem_base + (uint32_t)(a * BN);
+            const uint32_t tacc = tmem_base + (uint32_t)(a * MT * BN);
             for (int kb = 0; kb < num_k; ++kb, ++kbg) {
                 const int s = (int)(kbg % STAGES);
                 const uint32_t ph = (uint32_t)(kbg / STAGES) & 1;
@@ -187,13 +195,17 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (lane == 0) {
                     const uint32_t st = base + s * L::kStage;
-                    const uint32_t a_hi = st, a_lo = st + L::kA, b_hi = st + 2 * L::kA, b_lo = b_hi + L::kB;
+                    const uint32_t b_hi = st + MT * 2 * L::kA, b_lo = b_hi + L::kB;
 #pragma unroll
-                    for (int k4 = 0; k4 < (HN_GEMM_AB == 3 ? 0 : BK / 8); ++k4) {
-                        const uint32_t off = k4 * 32;   // 8 tf32 = 32 bytes inside the 128-byte swizzle row
-                        umma_tf32(tacc, umma_desc(a_hi + off), umma_desc(b_hi + off), idesc, (kb | k4) != 0);
-                        umma_tf32(tacc, umma_desc(a_hi + off), umma_desc(b_lo + off), idesc, 1);
-                        umma_tf32(tacc, umma_desc(a_lo + off), umma_desc(b_hi + off), idesc, 1);
+                    for (int h = 0; h < MT; ++h) {
+                        const uint32_t a_hi = st + h * 2 * L::kA, a_lo = a_hi + L::kA, th = tacc + (uint32_t)(h * BN);
+#pragma unroll
+                        for (int k4 = 0; k4 < (HN_GEMM_AB == 3 ? 0 : BK / 8); ++k4) {
+                            const uint32_t off = k4 * 32;   // 8 tf32 = 32 bytes inside the 128-byte swizzle row
+                            umma_tf32(th, umma_desc(a_hi + off), umma_desc(b_hi + off), idesc, (kb | k4) != 0);
+                            umma_tf32(th, umma_desc(a_hi + off), umma_desc(b_lo + off), idesc, 1);
+                            umma_tf32(th, umma_desc(a_lo + off), umma_desc(b_hi + off), idesc, 1);
+                        }
                     }
                     umma_commit(empty0 + 8 * s);                          // stage free once these MMAs retire
                     if (kb == num_k - 1) umma_commit(tfull0 + 8 * a);     // accumulator complete
@@ -209,8 +221,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 const int s = (int)(kbg % STAGES);
                 const uint32_t ph = (uint32_t)(kbg / STAGES) & 1;
                 mbar_wait(full0 + 8 * s, ph);
-                float4 *hi = reinterpret_cast<float4 *>(gen + s * L::kStage);
-                float4 *lo = reinterpret_cast<float4 *>(gen + s * L::kStage + L::kA);
+#pragma unroll
+                for (int sub = 0; sub < MT; ++sub) {
+                float4 *hi = reinterpret_cast<float4 *>(gen + s * L::kStage + sub * 2 * L::kA);
+                float4 *lo = reinterpret_cast<float4 *>(gen + s * L::kStage + sub * 2 * L::kA + L::kA);
 #pragma unroll
                 for (int i = 0; i < (HN_GEMM_AB == 1 ? 0 : L::kA / 16 / 128); ++i) {
                     const float4 v = hi[t + i * 128];
@@ -221,6 +235,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
                     hi[t + i * 128] = h;
                     lo[t + i * 128] = l;
+                }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
                 mbar_arrive(split0 + 8 * s);
@@ -241,21 +256,26 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         uint8_t *sC = gen + L::kStaging + grp * 16384;    // one staging tile per group
         const int bar_id = 1 + grp;
         long long it = 0;
+        constexpr int CH = BN / 64;                          // chunks of a sub-tile per group
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            const int n0 = (int)(tile % n_tiles_n) * BN, m0 = (int)(tile / n_tiles_n) * BM;
-            const long long row = (long long)m0 + rl;
+            const int n0 = (int)(tile % n_tiles_n) * BN, m0 = (int)(tile / n_tiles_n) * (BM * MT);
+            const int n_sub = min(MT, (M - m0 + BM - 1) / BM);       // sub-tiles with rows inside the matrix
             const int a = (int)(it & 1);
             float4 z[8];
-            if (mode == 2 && row < M) {         // pre-activations of the group's first chunk: in flight while the tile is multiplied
+            if (mode == 2 && (long long)m0 + rl < M) {      // pre-activations of the group's first chunk: in flight while the tile is multiplied
 #pragma unroll
-                for (int j = 0; j < 8; ++j) z[j] = __ldg(reinterpret_cast<const float4 *>(aux + row * ld_aux + n0 + grp * 32 + 4 * j));
+                for (int j = 0; j < 8; ++j)
+                    z[j] = __ldg(reinterpret_cast<const float4 *>(aux + ((long long)m0 + rl) * ld_aux + n0 + grp * 32 + 4 * j));
             }
             mbar_wait(tfull0 + 8 * a, (uint32_t)((it >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-            for (int c0 = grp * 32; c0 < BN; c0 += 64) {
+            for (int ci = 0; ci < n_sub * CH; ++ci) {
+                const int h = ci / CH, c0 = grp * 32 + (ci % CH) * 64;
+                const int mh = m0 + h * BM;
+                const long long row = (long long)mh + rl;
                 uint32_t r[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + c0);
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * MT * BN + h * BN + c0);
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
                     "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
@@ -265,7 +285,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                       "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (c0 + 64 >= BN) {       // this warp has read its share of the accumulator: hand it back to the MMA warp
+                if (ci + 1 == n_sub * CH) {       // this warp has read its share of the accumulators: hand them back to the MMA warp
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(tempty0 + 8 * a);            // (8 arrivals = all epilogue warps)
@@ -292,7 +312,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
                     if (t == 0) {
                         asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmC2),
-                                     "r"(smem_u32(sC)), "r"(n0 + c0), "r"(m0)
+                                     "r"(smem_u32(sC)), "r"(n0 + c0), "r"(mh)
                                      : "memory");
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
@@ -308,10 +328,14 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         for (int j = 0; j < 8; ++j) {
                             o[j].x *= dssilu(z[j].x); o[j].y *= dssilu(z[j].y); o[j].z *= dssilu(z[j].z); o[j].w *= dssilu(z[j].w);
                         }
-                        if (c0 + 64 < BN) {     // next chunk's pre-activations
+                    }
+                    if (ci + 1 < n_sub * CH) {     // next chunk's pre-activations
+                        const int hn = (ci + 1) / CH, cn = grp * 32 + ((ci + 1) % CH) * 64;
+                        const long long rn = (long long)m0 + hn * BM + rl;
+                        if (rn < M) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j)
-                                z[j] = __ldg(reinterpret_cast<const float4 *>(aux + row * ld_aux + n0 + c0 + 64 + 4 * j));
+                                z[j] = __ldg(reinterpret_cast<const float4 *>(aux + rn * ld_aux + n0 + cn + 4 * j));
                         }
                     }
                 }
@@ -326,7 +350,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
                 if (t == 0) {
                     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(&tmC),
-                                 "r"(smem_u32(sC)), "r"(n0 + c0), "r"(m0)
+                                 "r"(smem_u32(sC)), "r"(n0 + c0), "r"(mh)
                                  : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
@@ -337,7 +361,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 2) {
-        constexpr uint32_t cols = 2 * BN;
+        constexpr uint32_t cols = 2 * MT * BN;
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(cols));
     }
 }
@@ -386,7 +410,7 @@ int launch(const float *A, int64_t M, int64_t K, int64_t lda, const float *Whi, 
     else tc2 = tc;
     // (a per-device attribute: set on every launch instead of remembering it in library state)
     HN_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN>::kTotal), where);
-    const long long tiles = (N / BN) * ((M + BM - 1) / BM);
+    const long long tiles = (N / BN) * ((M + BM * MT - 1) / (BM * MT));
     const int sms = hn::num_sms() > 0 ? hn::num_sms() : 148;
     dim3 grid((unsigned)(tiles < sms ? tiles : sms));
     gemm_tf32x3_kernel<BN><<<grid, 512, Smem<BN>::kTotal, st>>>(ta, tbh, tbl, tc, tc2, bias, C, (int)M, (int)N, (int)K, (long long)ldc, mode, aux,
