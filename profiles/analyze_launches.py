@@ -19,6 +19,10 @@ def load(path):
         if t:
             out.append((["edge_tc_fwd", "edge_tc_bwd_dst", "edge_tc_bwd_src"][int(t.group(1))], v))
             continue
+        t = re.search(r"(layer0_basis_kernel|layernorm_kernel|readout_kernel)<(?:\(bool\))?(?:\d+, )?(?:\(bool\))?(\d|true|false)>", name)
+        if t:
+            out.append((t.group(1).replace("_kernel", "") + ("_bwd" if t.group(2) in ("1", "true") else "_fwd"), v))
+            continue
         m = re.search(r"(gemm_tf32x3_kernel|node_\w+_kernel|halo_\w+_kernel|tile_windows_kernel|split_weights_kernel|plan_\w+_kernel|"
                       r"basis_index_kernel|split_tf32\w*_kernel)", name)
         if m:
