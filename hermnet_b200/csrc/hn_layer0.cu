@@ -55,8 +55,8 @@ __device__ __forceinline__ float transpose_reduce16(float (&val)[16], int lane) 
 
 // Shared memory: Gaussian centres [K] | per warp: S[4 weights (1, ux, uy, uz)][KP] + 64 scratch floats.
 // Edges are read 32 at a time (one per lane, coalesced) and broadcast with shuffles; the per-edge body is branch-free (lanes
-// without a band position update a private scratch word), so the warp stays converged and its shared-memory updates of
-// successive edges -- which may hit the same word from different lanes -- execute in program order.
+// without a band position update a private scratch word) and ends in __syncwarp(): the shared-memory updates of successive
+// edges may hit the same word from different lanes.
 template <bool BWD>
 __global__ void __launch_bounds__(32 * kWarps) layer0_basis_kernel(L0Args A, float *__restrict__ Sa, float *__restrict__ Sc,
                                                                    const float *__restrict__ gSa, const float *__restrict__ gSc,
@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(32 * kWarps) layer0_basis_kernel(L0Args A, flo
                 float *q1 = cnt ? s1 + cnt0 + max(z, 0) : (valid ? s1 + idx : scratch + 32);
                 *q0 = fmaf(v, w0, *q0);
                 *q1 = fmaf(v, w1, *q1);
+                __syncwarp();      // the next edge's band may touch these words from other lanes (racecheck-clean ordering)
             }
         } else {
             for (int j4 = 0; j4 < nb; j4 += 4) {
