@@ -99,7 +99,7 @@ def _tiles(order, kc, grp_ptr, n_groups, num_rbf, rec, grp_mod):
     torch.cumsum(counts, 0, dtype=torch.int32, out=grp_tile[1:])
     n_tiles, n_live = torch.stack([grp_tile[-1], grp_ptr[n_groups]]).tolist()       # one host sync per plan
     tile_start = ops.tc_plan_fill(order, kc, grp_ptr, n_groups, num_rbf, grp_tile, n_tiles, window)
-    tile_mod = torch.repeat_interleave(grp_mod.to(torch.int32), counts.long()).contiguous() if n_tiles else \
+    tile_mod = torch.repeat_interleave(grp_mod.to(torch.int32), counts.long(), output_size=n_tiles).contiguous() if n_tiles else \
         torch.zeros(1, dtype=torch.int32, device=dev)
     erec, tile_info = ops.tc_plan_finalize(order, tile_start, n_tiles, n_live, rec, tile_mod)
     return grp_tile, tile_info, erec, n_tiles, window, n_live
@@ -150,7 +150,7 @@ def build_dst_plan(g, geom: Tensor, inv_rc: float, num_rbf: int) -> TilePlan:
     blk_info = torch.stack([row0.reshape(-1), torch.full((n_blocks,), rpa, device=dev, dtype=torch.long),
                             chunk_size.view(-1, 1).expand(-1, rpa).reshape(-1), blk_mod], 1).to(torch.int32).contiguous()
     # per atom: chunk and position inside it
-    atom_chunk = torch.repeat_interleave(torch.arange(n_chunks, device=dev), chunk_size.long())
+    atom_chunk = torch.repeat_interleave(torch.arange(n_chunks, device=dev), chunk_size.long(), output_size=n)
     atom_local = torch.arange(n, device=dev) - chunk_atom0[atom_chunk]
     rec, kc, sub = ops.tc_plan_records(g, geom, inv_rc, num_rbf, False, atom_local.to(torch.int32).contiguous(), 1)
     if rpa == 1 and n_blocks > 0 and num_rbf <= 8192:
@@ -175,7 +175,7 @@ def build_dst_plan(g, geom: Tensor, inv_rc: float, num_rbf: int) -> TilePlan:
         seg_len = (seg_hi - seg_lo).clamp(min=1).double()
         frac = (idx_in_seg.double() * R + 0.5 * R) / seg_len[seg_of_chunk]
         key = frac.view(-1, 1).expand(-1, rpa).reshape(-1)
-        plan.blk_order = torch.sort(key, stable=True).indices.to(torch.int32).to(dev).contiguous()
+        plan.blk_order = torch.sort(key.to(dev), stable=True).indices.to(torch.int32).contiguous()     # (device sort: ~0.1 ms)
     return plan
 
 
@@ -219,7 +219,7 @@ def build_src_plan(g, geom: Tensor, inv_rc: float, num_rbf: int) -> TilePlan:
         seg = torch.clamp(torch.searchsorted(tp, first, right=True) - 1, 0, len(g.type_ptr) - 2)
         lo_, hi_ = tp[seg], tp[seg + 1]
         key = (first - lo_) / (hi_ - lo_).clamp(min=1.0)
-        plan.blk_order = torch.sort(key, stable=True).indices.to(torch.int32).to(dev).contiguous()
+        plan.blk_order = torch.sort(key.to(dev), stable=True).indices.to(torch.int32).contiguous()
     return plan
 
 
