@@ -53,7 +53,7 @@ __device__ __forceinline__ float transpose_reduce16(float (&val)[16], int lane) 
     return val[0] + __shfl_xor_sync(0xffffffffu, val[0], 16);
 }
 
-// Shared memory: Gaussian centres [K] | per warp: S[4 weights (1, ux, uy, uz)][KP] + 64 scratch floats.
+// Shared memory: Gaussian centres [K] | per warp (forward): S[4 weights (1, ux, uy, uz)][KP + 8] + 64 scratch floats.
 // Edges are read 32 at a time (one per lane, coalesced) and broadcast with shuffles; the per-edge body is branch-free (lanes
 // without a band position update a private scratch word) and ends in __syncwarp(): the shared-memory updates of successive
 // edges may hit the same word from different lanes.
@@ -72,8 +72,11 @@ __global__ void __launch_bounds__(32 * kWarps) layer0_basis_kernel(L0Args A, flo
     if (row >= A.n_rows) return;
     // forward: the row's sums live in shared memory (read-modify-write per edge); backward: the g_S row is only read (48 words per
     // edge out of 4 KP) -- straight from global memory / L1, which leaves the occupancy to the registers
-    float *S = offs + koff + (BWD ? 0 : (size_t)warp * (4 * KP + 64));
-    float *scratch = S + 4 * KP + lane;
+    // (row stride KP + 8 words: the two halves of the warp update rows 2 apart at the same column -- 2 (KP + 8) = 16 mod 32 puts
+    // them on disjoint banks; with stride KP every update was a 2-way bank conflict and the L1 data pipe, at 78 %, set the time)
+    const int KPs = KP + 8;
+    float *S = offs + koff + (BWD ? 0 : (size_t)warp * (4 * KPs + 64));
+    float *scratch = S + 4 * KPs + lane;
     const int e0 = __ldg(A.rowptr + row), e1 = __ldg(A.rowptr + row + 1);
     if (__ldg(A.row_mod + row) < 0) {
         if (BWD)
@@ -82,13 +85,13 @@ __global__ void __launch_bounds__(32 * kWarps) layer0_basis_kernel(L0Args A, flo
     }
     const int n4 = KP >> 2;
     if (!BWD) {
-        for (int i = lane; i < 4 * n4 + 16; i += 32) reinterpret_cast<float4 *>(S)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = lane; i < KPs + 16; i += 32) reinterpret_cast<float4 *>(S)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         __syncwarp();
     }
     const int kk = lane & 15, half = lane >> 4;
     const int cnt0 = A.nz * K;
     const float cl2 = A.coeff * 1.4426950408889634f;
-    float *s0 = S + (2 * half) * KP, *s1 = s0 + KP;        // the two sums this lane owns: half 0 (1, ux), half 1 (uy, uz)
+    float *s0 = S + (2 * half) * KPs, *s1 = s0 + KPs;      // the two sums this lane owns: half 0 (1, ux), half 1 (uy, uz)
     const float *gc = BWD ? gSc + (size_t)row * 3 * KP : nullptr;
     const float *g0 = BWD ? (half == 0 ? gSa + (size_t)row * KP : gc + KP) : nullptr, *g1 = BWD ? (half == 0 ? gc : gc + 2 * KP) : nullptr;
     for (int eb = e0; eb < e1; eb += 32) {
@@ -177,7 +180,9 @@ __global__ void __launch_bounds__(32 * kWarps) layer0_basis_kernel(L0Args A, flo
         float4 *oa = reinterpret_cast<float4 *>(Sa + (size_t)row * KP);
         float4 *oc = reinterpret_cast<float4 *>(Sc + (size_t)row * 3 * KP);
         for (int i = lane; i < n4; i += 32) oa[i] = reinterpret_cast<const float4 *>(S)[i];
-        for (int i = lane; i < 3 * n4; i += 32) oc[i] = reinterpret_cast<const float4 *>(S)[n4 + i];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            for (int i = lane; i < n4; i += 32) oc[c * n4 + i] = reinterpret_cast<const float4 *>(S + (1 + c) * KPs)[i];
     }
 }
 
@@ -186,7 +191,7 @@ int check(const char *where, const hn_edge_params *p, int32_t n_elem, int32_t kp
     HN_REQUIRE(p->n_rows >= 0 && p->num_rbf >= 2 && p->env_p >= 1, where, "bad sizes");
     HN_REQUIRE(n_elem >= 1 && n_elem <= 255 && kp % 4 == 0 && (int64_t)kp >= (int64_t)n_elem * (p->num_rbf + 1), where,
                "row length must be a multiple of 4 and hold n_elem * (num_rbf + 1) sums");
-    HN_REQUIRE((int64_t)kWarps * (4 * kp + 64) * 4 + 4 * (int64_t)p->num_rbf <= 200 * 1024, where, "row too long for shared memory");
+    HN_REQUIRE((int64_t)kWarps * (4 * (kp + 8) + 64) * 4 + 4 * (int64_t)p->num_rbf <= 200 * 1024, where, "row too long for shared memory");
     return 0;
 }
 
@@ -202,7 +207,7 @@ int launch(const char *where, const hn_edge_params *p, const int32_t *rowptr, co
     a.offset = offset; a.n_rows = p->n_rows; a.K = p->num_rbf; a.nz = n_elem; a.KP = kp; a.env_p = p->env_p;
     a.inv_rc = p->inv_rc; a.coeff = p->coeff;
     HN_REQUIRE(!(p->flags & 1) || live != nullptr, where, "a Verlet-skin list (flags bit 0) needs the live mask");
-    const size_t smem = ((BWD ? 0 : (size_t)kWarps * (4 * kp + 64)) + ((p->num_rbf + 3) & ~3)) * sizeof(float);
+    const size_t smem = ((BWD ? 0 : (size_t)kWarps * (4 * (kp + 8) + 64)) + ((p->num_rbf + 3) & ~3)) * sizeof(float);
     HN_CUDA(cudaFuncSetAttribute(layer0_basis_kernel<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), where);
     const unsigned blocks = (unsigned)((p->n_rows + kWarps - 1) / kWarps);
     layer0_basis_kernel<BWD><<<blocks, 32 * kWarps, smem, (cudaStream_t)stream>>>(a, Sa, Sc, gSa, gSc, reinterpret_cast<float4 *>(g_geom));
