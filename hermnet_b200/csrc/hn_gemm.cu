@@ -11,11 +11,7 @@
 // the dropped lo.lo term is <= 2^-22 relative.  W is split once on the host side; A is split in shared memory by the
 // CTA that consumes it (an elementwise op, so it is oblivious to the 128-byte swizzle TMA wrote).
 //
-// CTA = one 128 x BN output tile, 256 threads:
-//   warp 0   : TMA producer (A raw, W_hi, W_lo K-chunks of 32 floats = one 128-byte swizzle row), 3-stage ring
-//   warp 1   : MMA issuer (one thread), tcgen05.commit releases the stage / signals the epilogue
-//   warp 2   : TMEM allocation
-//   warps 4-7: split A in place (hi) + side buffer (lo), then epilogue: tcgen05.ld 32x32b -> +bias -> st.global
+// The kernel is a persistent, warp-specialised CTA per SM (roles and tile shape: see gemm_tf32x3_kernel below).
 #include <cuda.h>
 
 #include "hn_common.cuh"
