@@ -34,7 +34,8 @@ class _GatherRows(Function):
     def forward(ctx, X: Tensor, seg: Segments):
         ctx.seg = seg
         ctx.shape = X.shape
-        return ops.gather_rows(X.reshape(X.size(0), -1).contiguous(), seg.index).view((-1,) + tuple(X.shape[1:]))
+        cols = math.prod(X.shape[1:])          # (explicit sizes: -1 is ambiguous for empty tensors, e.g. a graph without edges)
+        return ops.gather_rows(X.reshape(X.size(0), cols).contiguous(), seg.index).view((seg.index.numel(),) + tuple(X.shape[1:]))
 
     @staticmethod
     def backward(ctx, g):
@@ -45,7 +46,7 @@ class _SegmentSum(Function):
     @staticmethod
     def forward(ctx, Y: Tensor, seg: Segments):
         ctx.seg = seg
-        out = ops.segment_sum(Y.reshape(Y.size(0), -1).contiguous(), seg.rowptr, seg.perm, seg.n_rows)
+        out = ops.segment_sum(Y.reshape(Y.size(0), math.prod(Y.shape[1:])).contiguous(), seg.rowptr, seg.perm, seg.n_rows)
         return out.view((seg.n_rows,) + tuple(Y.shape[1:]))
 
     @staticmethod

@@ -214,6 +214,13 @@ class _HermNet(nn.Module):
         if self.intensive and halo is None:
             # (domain decomposition: a rank only holds a partial sum -- DomainDecomposition divides by the GLOBAL count)
             energy = energy / (sb.rowptr[1:] - sb.rowptr[:-1])[: g.n_graphs].clamp(min=1).to(energy.dtype)
+        if g.n_edges == 0 and torch.is_grad_enabled():
+            # no atom has a neighbour: the energy does not depend on the geometry.  The reference still returns it attached to
+            # pos / cell through empty edge tensors (hermnet.py:136-148), so callers get ZERO forces from autograd.grad
+            # (calculator.py:77-83) instead of an "unused input" error -- keep that
+            for t in (pos, cell):
+                if t is not None and t.requires_grad:
+                    energy = energy + 0.0 * t.sum()
         return energy, x, vec
 
     # ------------------------------------------------------------------------------------------------

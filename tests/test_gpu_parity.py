@@ -391,3 +391,21 @@ def test_halo_pack_unpack_kernels():
     ops.halo_unpack(bufs[0], ghost, x2, v2.view(n, 3 * F))
     assert torch.equal(x2[300:390], bufs[0][:, :F]) and torch.equal(v2[300:390].reshape(90, 3 * F), bufs[0][:, F:])
     assert torch.equal(x2[:300], x[:300]) and torch.equal(v2[390:], vec[390:])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("edge_path", ["fused", "composite"])
+def test_system_without_edges_on_gpu(edge_path):
+    """Isolated atoms (E = 0): every kernel of the path must accept empty edge arrays; energy finite, forces exactly zero."""
+    from tests.util import lattice_system
+    pos, Z, cell = lattice_system(3, [3, 8], 4, a=6.0, jitter=0.0)
+    torch.manual_seed(1)
+    model = H.HVNet(elems=["Li", "O"], rc=3.0, num_layers=2, hidden_channels=128, num_rbf=16).to("cuda:0").eval()
+    for p in model.parameters():
+        p.requires_grad_(False)
+    model.edge_path = edge_path
+    d = H.Data(pos=pos.cuda().requires_grad_(True), atomic_number=Z.cuda(), cell=cell.cuda().requires_grad_(True))
+    e = model(d)
+    assert d.graph.n_edges == 0 and torch.isfinite(e).all()
+    gp, gc = torch.autograd.grad(e.sum(), [d.pos, d.cell])
+    assert float(gp.abs().max()) == 0.0 and float(gc.abs().max()) == 0.0

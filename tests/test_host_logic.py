@@ -306,3 +306,28 @@ def test_graph_and_plans_are_released_without_the_garbage_collector(emu, kind, e
         assert wg() is None and wp() is None
     finally:
         gc.enable()
+
+
+@pytest.mark.parametrize("fused_node,edge_path,frozen", [(True, "fused", True), (False, "fused", True), (False, "composite", True),
+                                                         (False, "composite", False)])
+def test_system_without_edges_gives_zero_forces(emu, fused_node, edge_path, frozen):
+    """Isolated atoms (nothing within rc): like the reference, the energy stays attached to pos / cell and autograd.grad
+    returns zeros (calculator.py:77-83 calls it without allow_unused) on every formulation."""
+    from tests.util import lattice_system
+    pos, Z, cell = lattice_system(3, [3, 8], 4, a=6.0, jitter=0.0)
+    torch.manual_seed(1)
+    model = H.HVNet(elems=["Li", "O"], rc=3.0, num_layers=2, hidden_channels=64, num_rbf=16).eval()
+    for p in model.parameters():
+        p.requires_grad_(not frozen)
+    model.fused_node, model.edge_path = fused_node, edge_path
+    d = H.Data(pos=pos.clone().requires_grad_(True), atomic_number=Z, cell=cell.clone().requires_grad_(True))
+    e = model(d)
+    assert d.graph.n_edges == 0 and torch.isfinite(e).all()
+    gp, gc = torch.autograd.grad(e.sum(), [d.pos, d.cell])
+    assert float(gp.abs().max()) == 0.0 and float(gc.abs().max()) == 0.0
+    # the atomic energies are those of the bare embeddings pushed through the residual / update blocks: same on every path
+    model.fused_node, model.edge_path = True, "fused"
+    for p in model.parameters():
+        p.requires_grad_(False)
+    e_ref = model(H.Data(pos=pos.clone(), atomic_number=Z, cell=cell.clone()))
+    assert torch.allclose(e.detach(), e_ref, rtol=1e-5, atol=1e-6)
